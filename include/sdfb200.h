@@ -1,0 +1,252 @@
+/*
+ * sdfb200.h -- C ABI of the B200-native SDF volume-rendering hot path (sdfstudio drop-in).
+ *
+ * The reference (autonomousvision/sdfstudio) has NO native/FFI boundary on this path: its plug points are Python
+ * nn.Modules.  This header is the C-ABI *underneath* those modules; every entry point names the
+ * reference function it replaces (paths relative to the reference root).  The Python host side
+ * (sdfstudio_b200/*.py) mirrors the reference classes and binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch / C++ types cross the boundary.  All pointers are DEVICE pointers unless a
+ *     parameter is documented as host.  Tensors are dense row-major fp32 unless stated.
+ *   - ownership: the caller allocates every buffer including workspace (size-query functions are provided); the
+ *     library never allocates, frees or retains a pointer past the call.
+ *   - every call only enqueues work on `stream` (a cudaStream_t passed as void*); no hidden synchronisation.
+ *   - return value: 0 = ok, <0 = invalid argument (SDFB200_E*), >0 = cudaError_t.  No exceptions, no abort.
+ *     sdfb200_last_error_string() returns a thread-local description of the last failure.
+ *   - re-entrant and stateless apart from immutable per-device kernel attributes set once.
+ */
+#ifndef SDFB200_H_
+#define SDFB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDFB200_VERSION 100
+#define SDFB200_MAX_LEVELS 32
+#define SDFB200_MAX_LAYERS 12
+
+enum {
+  SDFB200_OK = 0,
+  SDFB200_EINVAL = -1,      /* bad argument / unsupported configuration */
+  SDFB200_EWORKSPACE = -2,  /* workspace too small */
+  SDFB200_EUNSUPPORTED = -3
+};
+
+enum { SDFB200_GRID_TORCH = 0, SDFB200_GRID_TCNN = 1 };      /* table layout */
+enum { SDFB200_DT_F32 = 0, SDFB200_DT_F16 = 1 };             /* table element type */
+enum { SDFB200_CONTRACT_NONE = 0, SDFB200_CONTRACT_LINF = 1, SDFB200_CONTRACT_L2 = 2 };
+enum { SDFB200_SPACING_UNIFORM = 0, SDFB200_SPACING_LINDISP = 1, SDFB200_SPACING_SQRT = 2, SDFB200_SPACING_LOG = 3,
+       SDFB200_SPACING_PIECEWISE = 4, SDFB200_SPACING_IDENTITY = 5 /* bins already euclidean */ };
+enum { SDFB200_BG_COLOR = 0, SDFB200_BG_LAST_SAMPLE = 1, SDFB200_BG_PER_RAY = 2 };
+enum { SDFB200_PRECISION_FP32 = 0,      /* CUDA-core fp32 FMA (exact-fp32 reference numerics)            */
+       SDFB200_PRECISION_BF16X3 = 1,    /* tcgen05 bf16 split a0*w0 + a1*w0 + a0*w1, fp32 accumulate      */
+       SDFB200_PRECISION_BF16 = 2 };    /* tcgen05 single bf16 pass (fast mode; reported with PSNR-vs-ref) */
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-resolution grid.  Replaces tinycudann.Encoding(HashGrid) as configured at
+ * nerfstudio/fields/sdf_field.py:230-241 and HashEncoding.pytorch_fwd (field_components/encodings.py:357-398).
+ * Filled by the host (sdfstudio_b200/encoding.py).  `scale`: per-level coordinate scale; torch layout: corner =
+ * ceil/floor(x*scale), every level hashed, offset = l*2^log2_hashmap_size; tcnn layout: pos = x*scale+0.5,
+ * `resolution`/`size`/`hashed` per level.  `offset` counts table ENTRIES (rows of n_features values).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct sdfb200_grid {
+  int32_t layout;            /* SDFB200_GRID_* */
+  int32_t n_levels;          /* <= SDFB200_MAX_LEVELS */
+  int32_t n_features;        /* 1, 2, 4 or 8 */
+  int32_t log2_hashmap_size;
+  int32_t smoothstep;        /* 0 linear, 1 smoothstep (t*t*(3-2t)) */
+  int32_t active_levels;     /* levels >= this are zeroed: SDFField.update_mask (sdf_field.py:376-378) */
+  int32_t table_dtype;       /* SDFB200_DT_* */
+  int32_t reserved;
+  float scale[SDFB200_MAX_LEVELS];
+  uint32_t resolution[SDFB200_MAX_LEVELS];
+  uint32_t size[SDFB200_MAX_LEVELS];
+  uint64_t offset[SDFB200_MAX_LEVELS];
+  uint8_t hashed[SDFB200_MAX_LEVELS];
+} sdfb200_grid_t;
+
+/* tcnn.Encoding.forward / HashEncoding.pytorch_fwd: x01 [n,3] in [0,1] -> out [n, L*F] (masked levels = 0).
+ * dout_dx (optional, may be NULL): [n, L*F, 3] = d out / d x01.  out_ld = row stride of `out` in floats. */
+int sdfb200_grid_encode(const sdfb200_grid_t* grid, const void* table, const float* x01, int64_t n, float* out,
+                        int64_t out_ld, float* dout_dx, void* stream);
+
+/* backward of the above w.r.t. the table (atomic scatter-add into dtable, fp32, same row layout as the table) and,
+ * optionally, w.r.t. x01 (dx01 [n,3], may be NULL).  dout [n, L*F]. */
+int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
+                                 int64_t n, float* dtable, float* dx01, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * SDFField.  Replaces nerfstudio/fields/sdf_field.py: forward_geonetwork :380-410, gradient :424-465, get_alpha
+ * :476-525, get_colors :532-612, get_outputs :614-689, LaplaceDensity :57-66, get_occupancy :527-530,
+ * NeRFEncoding.forward (encodings.py:167-208) and SceneContraction.forward (spatial_distortions.py:66-73).
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct sdfb200_field {
+  sdfb200_grid_t grid;
+  int32_t use_grid_feature;
+  int32_t pe_degree;              /* position_encoding_max_degree */
+  int32_t use_position_encoding;  /* 0 => PE block is zeros (sdf_field.py:393-394) */
+  int32_t off_axis;               /* 21-direction off-axis PE (encodings.py:129-153,191-192) */
+  int32_t contraction;            /* SDFB200_CONTRACT_* (spatial_distortion passed to SDFField) */
+  int32_t n_geo_linear;           /* num_layers + 1 */
+  int32_t geo_dims[SDFB200_MAX_LAYERS + 1]; /* dims[0..n_geo_linear]; dims[0] = 3+pe+grid */
+  int32_t geo_skip_layer;         /* index l whose input is cat(h, inputs)/sqrt(2) (skip_in=[4]); -1 = none */
+  int32_t n_color_linear;         /* num_layers_color + 1 */
+  int32_t color_dims[SDFB200_MAX_LAYERS + 1];
+  int32_t appearance_dim;
+  int32_t use_diffuse_color, use_specular_tint, use_reflections, use_n_dot_v;
+  int32_t use_numerical_gradients;
+  float rgb_padding;
+  int32_t precision;              /* SDFB200_PRECISION_* */
+} sdfb200_field_t;
+
+/* raw (un-packed) parameter pointers, fp32, reference layout (nn.Linear weight [out,in] row-major).
+ * weight_g may be NULL for a layer without weight-norm (then weight_v is the plain weight). */
+typedef struct sdfb200_field_params {
+  const float* geo_weight_v[SDFB200_MAX_LAYERS];
+  const float* geo_weight_g[SDFB200_MAX_LAYERS];
+  const float* geo_bias[SDFB200_MAX_LAYERS];
+  const float* color_weight_v[SDFB200_MAX_LAYERS];
+  const float* color_weight_g[SDFB200_MAX_LAYERS];
+  const float* color_bias[SDFB200_MAX_LAYERS];
+  const float* diffuse_weight;  const float* diffuse_bias;   /* [3,geo_feat], [3] or NULL */
+  const float* tint_weight;     const float* tint_bias;
+} sdfb200_field_params_t;
+
+/* bytes of the packed-weight blob for this field (weight-norm folded, padded, bf16 split planes when a tensor-core
+ * precision is selected). */
+size_t sdfb200_field_packed_bytes(const sdfb200_field_t* f);
+/* fold weight-norm (W = g*v/||v||, sdf_field.py:312-313,360-361) and write the packed blob.  Call again whenever the
+ * parameters change. */
+int sdfb200_field_pack(const sdfb200_field_t* f, const sdfb200_field_params_t* p, void* packed, void* stream);
+
+typedef struct sdfb200_field_in {
+  int64_t n_rays;
+  int32_t n_samples;             /* samples per ray; N = n_rays*n_samples.  Point mode: n_samples=1, bins=NULL */
+  int32_t apply_contraction;     /* get_outputs contracts (:629-630); get_sdf / get_density do not (:412-418) */
+  const float* origins;          /* [R,3] (point mode: the points)                         */
+  const float* directions;       /* [R,3] or NULL when no colour/alpha output is requested */
+  const float* bins;             /* [R, S+1] euclidean bin edges; starts=bins[:, :-1], deltas=bins[:,1:]-bins[:,:-1] */
+  const float* appearance;       /* [R, appearance_dim] embedded appearance per ray, or NULL (= zeros)  */
+  const float* variance;         /* device ptr to deviation_network.variance (1 float) or NULL           */
+  const float* beta;             /* device ptr to laplace_density.beta (1 float) or NULL                 */
+  const float* beta_min;         /* device ptr to laplace_density.beta_min                               */
+  float cos_anneal_ratio;        /* SDFField._cos_anneal_ratio                                           */
+  float numerical_delta;         /* SDFField.numerical_gradients_delta                                   */
+} sdfb200_field_in_t;
+
+/* any NULL output is skipped, and stages nobody consumes are not run (e.g. only `sdf` => geo forward only). */
+typedef struct sdfb200_field_out {
+  float* sdf;          /* [N]      FieldHeadNames.SDF        */
+  float* geo_feature;  /* [N, geo_feat_dim]  (forward_geonetwork()[:,1:]) */
+  float* gradients;    /* [N,3]    FieldHeadNames.GRADIENT   */
+  float* normals;      /* [N,3]    FieldHeadNames.NORMAL     */
+  float* rgb;          /* [N,3]    FieldHeadNames.RGB        */
+  float* density;      /* [N]      FieldHeadNames.DENSITY    */
+  float* alpha;        /* [N]      FieldHeadNames.ALPHA      */
+  float* occupancy;    /* [N]      FieldHeadNames.OCCUPANCY  */
+  float* points_norm;  /* [N]      "points_norm"             */
+  float* sampled_sdf;  /* [N,6]    "sampled_sdf" (numerical gradients only) */
+  float* points;       /* [N,3]    the (contracted) sample positions  */
+} sdfb200_field_out_t;
+
+size_t sdfb200_field_workspace_bytes(const sdfb200_field_t* f, int64_t n_points);
+int sdfb200_field_forward(const sdfb200_field_t* f, const void* packed, const void* table, const sdfb200_field_in_t* in,
+                          const sdfb200_field_out_t* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Ray samplers.  Replace nerfstudio/model_components/ray_samplers.py.  A sample set is a pair of bin-edge buffers
+ * [R, S+1]: `spacing` (normalised) and `euclid` (distance along the ray), cf. cameras/rays.py:295-339.
+ * ------------------------------------------------------------------------------------------------------------- */
+/* SpacedSampler.generate_ray_samples :80-127.  base_bins [S+1] = linspace(0,1,S+1) (host computes it so that the
+ * values are bit-identical to torch.linspace); jitter: NULL (eval) or [R,1] / [R,S+1] uniform randoms (training). */
+int sdfb200_spaced_bins(const float* nears, const float* fars, const float* base_bins, const float* jitter,
+                        int32_t jitter_per_bin, int64_t n_rays, int32_t n_samples, int32_t spacing, float* spacing_bins,
+                        float* euclid_bins, void* stream);
+
+/* spacing -> euclidean map of an existing bin buffer: spacing_fn_inv(x*s_far + (1-x)*s_near)  (:115-117) */
+int sdfb200_bins_to_euclid(const float* spacing_bins, const float* nears, const float* fars, int64_t n_rays,
+                           int32_t n_bins, int32_t spacing, float* euclid_bins, void* stream);
+
+/* PDFSampler.generate_ray_samples :275-370.  weights [R,S_in] (the [...,0] slice), existing spacing bins [R,S_in+1],
+ * u [S_out+1] = the eval-mode u grid (host: torch.linspace(...)+1/(2*nb)) or the stratified base; jitter NULL or
+ * [R,1] / [R,S_out+1] (already divided by num_bins by the host: u + rand/num_bins).  Outputs: new spacing bins
+ * [R,S_out+1] (sorted-merged with the originals when include_original: [R, S_in+S_out+2]) and, optionally, the
+ * searchsorted indices `inds` [R,S_out+1] (int64, side="right"; may be NULL). */
+int sdfb200_pdf_sample(const float* weights, const float* existing_bins, const float* u, const float* jitter,
+                       int32_t jitter_per_bin, int64_t n_rays, int32_t s_in, int32_t s_out, float histogram_padding,
+                       float eps, int32_t include_original, float* new_bins, int64_t* inds, void* stream);
+
+/* ErrorBoundedSampler.merge_ray_samples :758-788: stable merge of the starts of two sample sets (spacing domain).
+ * bins_a [R,Sa+1], bins_b [R,Sb+1] -> merged [R,Sa+Sb+1], sorted_index [R,Sa+Sb] (int64; indices into cat(a,b)). */
+int sdfb200_merge_bins(const float* bins_a, const float* bins_b, int64_t n_rays, int32_t sa, int32_t sb, float* merged,
+                       int64_t* sorted_index, void* stream);
+/* torch.gather(cat([sdf_a, sdf_b], -1), 1, sorted_index) (:872-874, :646-648) */
+int sdfb200_merge_gather(const float* a, const float* b, const int64_t* sorted_index, int64_t n_rays, int32_t sa,
+                         int32_t sb, float* out, void* stream);
+
+/* NeuSSampler.rendering_sdf_with_fixed_inv_s :909-944 fused with RaySamples.get_weights_from_alphas
+ * (cameras/rays.py:194-210) and the zero pad (:885): euclid bins [R,S+1], sdf [R,S] -> weights [R,S] (last = 0). */
+int sdfb200_neus_upsample_weights(const float* euclid_bins, const float* sdf, int64_t n_rays, int32_t n_samples,
+                                  float inv_s, float* weights, void* stream);
+
+/* ErrorBoundedSampler inner step (:650-676): get_dstar :704-726, get_updated_beta :728-738 (beta_iters bisection
+ * steps of get_error_bound :740-756), LaplaceDensity with per-ray beta, weights/transmittance, and the error-bound
+ * upsampling weights.  beta [R] in/out.  beta0: device ptr (1 float, already |beta|+beta_min).
+ * Outputs weights [R,S] (density weights), err_weights [R,S] (error-bound pdf). */
+int sdfb200_volsdf_step(const float* euclid_bins, const float* sdf, const float* beta0, float* beta, int64_t n_rays,
+                        int32_t n_samples, float eps, int32_t beta_iters, float* weights, float* err_weights,
+                        void* stream);
+/* initial beta from Lemma 2 (:629-633): sqrt( sum(deltas^2) / (4 log(1+eps)) ) */
+int sdfb200_volsdf_init_beta(const float* euclid_bins, int64_t n_rays, int32_t n_samples, float eps, float* beta,
+                             void* stream);
+
+/* UniSurfSampler surface search (:1027-1077): first +->- sign change along the marching samples, linear root, and
+ * the shrunk [near, far] interval.  Outputs: z [R] (NaN when no hit), hit [R] (uint8), new nears/fars [R]. */
+int sdfb200_unisurf_interval(const float* euclid_bins, const float* sdf, const float* nears, const float* fars,
+                             int64_t n_rays, int32_t n_samples, float delta, float* z, uint8_t* hit, float* new_nears,
+                             float* new_fars, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Weights + renderers.  Replace cameras/rays.py:131-230 and model_components/renderers.py (dense branch).
+ * ------------------------------------------------------------------------------------------------------------- */
+/* RaySamples.get_weights_and_transmittance_from_alphas: alphas [R,S] -> weights [R,S], transmittance [R,S+1] (NULL ok) */
+int sdfb200_weights_from_alphas(const float* alphas, int64_t n_rays, int32_t n_samples, float* weights,
+                                float* transmittance, void* stream);
+/* RaySamples.get_weights_and_transmittance: density [R,S], euclid bins [R,S+1] -> weights, transmittance [R,S] */
+int sdfb200_weights_from_density(const float* density, const float* euclid_bins, int64_t n_rays, int32_t n_samples,
+                                 float* weights, float* transmittance, void* stream);
+
+typedef struct sdfb200_render_out {
+  float* rgb;           /* [R,3]  RGBRenderer.forward :98-118                       */
+  float* depth;         /* [R]    DepthRenderer 'expected' :246-259 (before the global clip) or 'median' :233-245 */
+  float* normal;        /* [R,3]  SemanticRenderer :284-295                         */
+  float* accumulation;  /* [R]    AccumulationRenderer :171-197                     */
+  float* steps_minmax;  /* [2]    global min / max of steps (for the clip at :257); must be pre-set to {+inf,-inf} */
+} sdfb200_render_out_t;
+/* composites rgb [R,S,3] / normals [R,S,3] with weights [R,S] along each ray.  background: bg_mode COLOR -> bg [3];
+ * PER_RAY -> bg [R,3] (the "random" draw); LAST_SAMPLE.  clamp01: eval-mode clamp (:116-117).
+ * depth_median != 0 selects the median method. */
+int sdfb200_render(const float* weights, const float* rgb, const float* normals, const float* euclid_bins,
+                   const float* bg, int32_t bg_mode, int32_t clamp01, int32_t depth_median, int64_t n_rays,
+                   int32_t n_samples, const sdfb200_render_out_t* out, void* stream);
+/* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
+int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------*/
+int sdfb200_version(void);
+const char* sdfb200_last_error_string(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches). */
+int64_t sdfb200_launch_count(void);
+/* sizeof() of the ABI structs (0 grid, 1 field, 2 field_params, 3 field_in, 4 field_out, 5 render_out): lets a binding
+ * verify its struct mirrors before the first call. */
+size_t sdfb200_struct_size(int32_t which);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDFB200_H_ */

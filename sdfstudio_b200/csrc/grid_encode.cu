@@ -1,0 +1,182 @@
+// Stand-alone grid encode / backward kernels behind sdfb200_grid_encode{,_backward} (the tcnn.Encoding operator
+// boundary, nerfstudio/fields/sdf_field.py:230-241,386).  HBM/L2-gather bound: one thread per (point, level) so that
+// a warp covers 2 points x 16 levels and its F-wide outputs are written to consecutive addresses.
+#include "grid.cuh"
+
+namespace sdfb200 {
+
+template <typename T, int F, bool GRAD>
+__global__ void __launch_bounds__(256) k_grid_encode(const __grid_constant__ sdfb200_grid_t g, const void* __restrict__ table,
+                                                     const float* __restrict__ x01, int64_t n, float* __restrict__ out,
+                                                     int64_t out_ld, float* __restrict__ dout_dx) {
+  const int L = g.n_levels;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L) return;
+  const int64_t p = idx / L;
+  const int l = (int)(idx - p * L);
+  float o[F];
+  float d[F][3];
+  if (l < g.active_levels) {
+    const float x = __ldg(x01 + p * 3), y = __ldg(x01 + p * 3 + 1), z = __ldg(x01 + p * 3 + 2);
+    encode_level<T, F, GRAD>(g, table, l, x, y, z, o, d);
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      o[f] = 0.f;
+      d[f][0] = d[f][1] = d[f][2] = 0.f;
+    }
+  }
+  float* op = out + p * out_ld + l * F;
+#pragma unroll
+  for (int f = 0; f < F; ++f) op[f] = o[f];
+  if (GRAD) {
+    float* dp = dout_dx + (p * L * F + l * F) * 3;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      dp[f * 3 + 0] = d[f][0]; dp[f * 3 + 1] = d[f][1]; dp[f * 3 + 2] = d[f][2];
+    }
+  }
+}
+
+// backward: scatter dout into the table gradient, optional dx01.
+template <typename T, int F>
+__global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__ sdfb200_grid_t g, const void* __restrict__ table,
+                                                         const float* __restrict__ x01, const float* __restrict__ dout, int64_t n,
+                                                         float* __restrict__ dtable, float* __restrict__ dx01) {
+  const int L = g.n_levels;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L) return;
+  const int64_t p = idx / L;
+  const int l = (int)(idx - p * L);
+  if (l >= g.active_levels) return;
+  const float x = __ldg(x01 + p * 3), y = __ldg(x01 + p * 3 + 1), z = __ldg(x01 + p * 3 + 2);
+  float go[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) go[f] = __ldg(dout + p * L * F + l * F + f);
+  const float s = g.scale[l];
+  const uint64_t base = g.offset[l];
+  if (g.layout == SDFB200_GRID_TORCH) {
+    const float sx = x * s, sy = y * s, sz = z * s;
+    const float fxf = floorf(sx), fyf = floorf(sy), fzf = floorf(sz);
+    const uint32_t fc[3][2] = {{(uint32_t)(int)fxf, (uint32_t)(int)ceilf(sx)}, {(uint32_t)(int)fyf, (uint32_t)(int)ceilf(sy)}, {(uint32_t)(int)fzf, (uint32_t)(int)ceilf(sz)}};
+    float o[3] = {sx - fxf, sy - fyf, sz - fzf};
+    if (g.smoothstep)
+      for (int d = 0; d < 3; ++d) o[d] = o[d] * o[d] * (3.f - 2.f * o[d]);
+    const uint32_t mask = (1u << g.log2_hashmap_size) - 1u;
+    for (int c = 0; c < 8; ++c) {
+      const int bx = c & 1, by = (c >> 1) & 1, bz = (c >> 2) & 1;  // 1 = ceil corner (weight o), 0 = floor (1-o)
+      const float w = (bx ? o[0] : 1.f - o[0]) * (by ? o[1] : 1.f - o[1]) * (bz ? o[2] : 1.f - o[2]);
+      const uint32_t h = (fc[0][bx] ^ (fc[1][by] * kPrimeY) ^ (fc[2][bz] * kPrimeZ)) & mask;
+      float* dst = dtable + (base + h) * F;
+#pragma unroll
+      for (int f = 0; f < F; ++f) atomicAdd(dst + f, w * go[f]);
+    }
+  } else {
+    const uint32_t res = g.resolution[l], size = g.size[l];
+    const bool hashed = g.hashed[l];
+    float pz[3] = {fmaf(x, s, 0.5f), fmaf(y, s, 0.5f), fmaf(z, s, 0.5f)};
+    uint32_t cell[3];
+    float w[3];
+    for (int d = 0; d < 3; ++d) {
+      const float fl = floorf(pz[d]);
+      cell[d] = (uint32_t)(int)fl;
+      const float t = pz[d] - fl;
+      w[d] = g.smoothstep ? t * t * (3.f - 2.f * t) : t;
+    }
+    for (int c = 0; c < 8; ++c) {
+      const uint32_t ix = cell[0] + (c & 1), iy = cell[1] + ((c >> 1) & 1), iz = cell[2] + ((c >> 2) & 1);
+      const float wt = ((c & 1) ? w[0] : 1.f - w[0]) * ((c & 2) ? w[1] : 1.f - w[1]) * ((c & 4) ? w[2] : 1.f - w[2]);
+      uint32_t idx2 = hashed ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
+      idx2 %= size;
+      float* dst = dtable + (base + idx2) * F;
+#pragma unroll
+      for (int f = 0; f < F; ++f) atomicAdd(dst + f, wt * go[f]);
+    }
+  }
+  if (dx01 != nullptr) {
+    float o[F];
+    float d[F][3];
+    encode_level<T, F, true>(g, table, l, x, y, z, o, d);
+    float ax = 0.f, ay = 0.f, az = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      ax = fmaf(go[f], d[f][0], ax); ay = fmaf(go[f], d[f][1], ay); az = fmaf(go[f], d[f][2], az);
+    }
+    atomicAdd(dx01 + p * 3 + 0, ax); atomicAdd(dx01 + p * 3 + 1, ay); atomicAdd(dx01 + p * 3 + 2, az);
+  }
+}
+
+int validate_grid(const sdfb200_grid_t* g) {
+  SDFB_REQUIRE(g != nullptr, "grid descriptor is NULL");
+  SDFB_REQUIRE(g->n_levels >= 1 && g->n_levels <= SDFB200_MAX_LEVELS, "grid.n_levels out of range");
+  SDFB_REQUIRE(g->n_features == 1 || g->n_features == 2 || g->n_features == 4 || g->n_features == 8, "grid.n_features must be 1,2,4,8");
+  SDFB_REQUIRE(g->layout == SDFB200_GRID_TORCH || g->layout == SDFB200_GRID_TCNN, "grid.layout");
+  SDFB_REQUIRE(g->table_dtype == SDFB200_DT_F32 || g->table_dtype == SDFB200_DT_F16, "grid.table_dtype");
+  SDFB_REQUIRE(g->log2_hashmap_size >= 1 && g->log2_hashmap_size <= 31, "grid.log2_hashmap_size");
+  SDFB_REQUIRE(g->active_levels >= 0 && g->active_levels <= g->n_levels, "grid.active_levels");
+  return 0;
+}
+
+template <typename T, int F>
+static int launch_encode(const sdfb200_grid_t& g, const void* table, const float* x01, int64_t n, float* out, int64_t out_ld,
+                         float* dout_dx, cudaStream_t st) {
+  const int64_t total = n * g.n_levels;
+  const unsigned blocks = (unsigned)ceil_div(total, 256);
+  if (dout_dx)
+    k_grid_encode<T, F, true><<<blocks, 256, 0, st>>>(g, table, x01, n, out, out_ld, dout_dx);
+  else
+    k_grid_encode<T, F, false><<<blocks, 256, 0, st>>>(g, table, x01, n, out, out_ld, nullptr);
+  SDFB_LAUNCHED("k_grid_encode");
+  return 0;
+}
+
+template <typename T, int F>
+static int launch_encode_bwd(const sdfb200_grid_t& g, const void* table, const float* x01, const float* dout, int64_t n,
+                             float* dtable, float* dx01, cudaStream_t st) {
+  const int64_t total = n * g.n_levels;
+  k_grid_encode_bwd<T, F><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(g, table, x01, dout, n, dtable, dx01);
+  SDFB_LAUNCHED("k_grid_encode_bwd");
+  return 0;
+}
+
+#define SDFB_DISPATCH_GRID(g, FN, ...)                                                      \
+  do {                                                                                      \
+    const bool h__ = (g).table_dtype == SDFB200_DT_F16;                                     \
+    switch ((g).n_features) {                                                               \
+      case 1: return h__ ? FN<__half, 1>(__VA_ARGS__) : FN<float, 1>(__VA_ARGS__);          \
+      case 2: return h__ ? FN<__half, 2>(__VA_ARGS__) : FN<float, 2>(__VA_ARGS__);          \
+      case 4: return h__ ? FN<__half, 4>(__VA_ARGS__) : FN<float, 4>(__VA_ARGS__);          \
+      default: return h__ ? FN<__half, 8>(__VA_ARGS__) : FN<float, 8>(__VA_ARGS__);         \
+    }                                                                                       \
+  } while (0)
+
+int grid_encode(const sdfb200_grid_t& g, const void* table, const float* x01, int64_t n, float* out, int64_t out_ld,
+                float* dout_dx, cudaStream_t st) {
+  if (n == 0) return 0;
+  SDFB_DISPATCH_GRID(g, launch_encode, g, table, x01, n, out, out_ld, dout_dx, st);
+}
+
+}  // namespace sdfb200
+
+using namespace sdfb200;
+
+extern "C" int sdfb200_grid_encode(const sdfb200_grid_t* grid, const void* table, const float* x01, int64_t n, float* out,
+                                   int64_t out_ld, float* dout_dx, void* stream) {
+  int r = validate_grid(grid);
+  if (r) return r;
+  SDFB_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return 0;
+  SDFB_REQUIRE(table && x01 && out, "NULL pointer");
+  SDFB_REQUIRE(out_ld >= (int64_t)grid->n_levels * grid->n_features, "out_ld too small");
+  return grid_encode(*grid, table, x01, n, out, out_ld, dout_dx, (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
+                                            int64_t n, float* dtable, float* dx01, void* stream) {
+  int r = validate_grid(grid);
+  if (r) return r;
+  SDFB_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return 0;
+  SDFB_REQUIRE(table && x01 && dout && dtable, "NULL pointer");
+  SDFB_DISPATCH_GRID(*grid, launch_encode_bwd, *grid, table, x01, dout, n, dtable, dx01, (cudaStream_t)stream);
+}

@@ -1,0 +1,122 @@
+"""B200-native drop-ins for ``nerfstudio.model_components.renderers`` (dense branch): RGBRenderer :42-118,
+AccumulationRenderer :171-197, DepthRenderer :200-261, SemanticRenderer :284-295.  The per-ray reductions run in
+libsdfb200.so (csrc/render.cu, sdfb200_render).  ``render_all`` composites every per-ray output SurfaceModel.get_outputs
+asks for (models/base_surface_model.py:300-310) in ONE kernel launch.
+"""
+from typing import Optional, Union
+
+import torch
+from torch import nn
+
+from . import _lib
+from .rays import bins_of
+
+
+def _render(weights, rgb=None, normals=None, bins=None, background=None, clamp01=False, depth_method: Optional[str] = None,
+            want_acc=False, want_normal=False, clip_depth=True):
+    lib = _lib.load()
+    w = _lib.f32c(weights[..., 0])
+    R, S = w.shape
+    dev = w.device
+    out = _lib.RenderOut()
+    res = {}
+    bg_mode, bg_t = _lib.BG_COLOR, None
+    rgb_c = None
+    if rgb is not None:
+        rgb_c = _lib.f32c(rgb)
+        res["rgb"] = torch.empty(R, 3, device=dev, dtype=torch.float32)
+        out.rgb = res["rgb"].data_ptr()
+        if isinstance(background, str):
+            if background == "last_sample":
+                bg_mode = _lib.BG_LAST_SAMPLE
+            elif background == "random":
+                bg_mode, bg_t = _lib.BG_PER_RAY, torch.rand(R, 3, device=dev)
+            else:
+                raise ValueError(f"unknown background {background!r}")
+        else:
+            bg_t = _lib.f32c(torch.as_tensor(background, dtype=torch.float32).to(dev))
+            if bg_t.dim() == 2:
+                bg_mode = _lib.BG_PER_RAY
+    nrm_c = None
+    if want_normal:
+        nrm_c = _lib.f32c(normals)
+        res["normal"] = torch.empty(R, nrm_c.shape[-1], device=dev, dtype=torch.float32)
+        if nrm_c.shape[-1] != 3:
+            raise NotImplementedError("SemanticRenderer: only 3 channels (normals) are composited by the kernel")
+        out.normal = res["normal"].data_ptr()
+    if want_acc:
+        res["accumulation"] = torch.empty(R, device=dev, dtype=torch.float32)
+        out.accumulation = res["accumulation"].data_ptr()
+    mm = None
+    if depth_method is not None:
+        res["depth"] = torch.empty(R, device=dev, dtype=torch.float32)
+        out.depth = res["depth"].data_ptr()
+        mm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        out.steps_minmax = mm.data_ptr()
+    _lib.check(lib.sdfb200_render(_lib.ptr(w), _lib.ptr(rgb_c), _lib.ptr(nrm_c), _lib.ptr(bins), _lib.ptr(bg_t), bg_mode, int(clamp01),
+                                  int(depth_method == "median"), R, S, out, _lib.stream_ptr()), "sdfb200_render")
+    if depth_method == "expected" and clip_depth:
+        _lib.check(lib.sdfb200_depth_clip(out.depth, out.steps_minmax, R, _lib.stream_ptr()), "sdfb200_depth_clip")
+    if "depth" in res:
+        res["depth"] = res["depth"][:, None]
+    if "accumulation" in res:
+        res["accumulation"] = res["accumulation"][:, None]
+    return res
+
+
+class RGBRenderer(nn.Module):
+    """renderers.py:42-118 (``ray_indices`` / packed samples are out of scope)."""
+
+    def __init__(self, background_color: Union[str, torch.Tensor] = "random") -> None:
+        super().__init__()
+        self.background_color = background_color
+
+    @classmethod
+    def combine_rgb(cls, rgb, weights, background_color="random", ray_indices=None, num_rays=None):
+        if ray_indices is not None:
+            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        return _render(weights, rgb=rgb, background=background_color, clamp01=False)["rgb"]
+
+    def forward(self, rgb, weights, ray_indices=None, num_rays=None):
+        if ray_indices is not None:
+            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        return _render(weights, rgb=rgb, background=self.background_color, clamp01=not self.training)["rgb"]
+
+
+class AccumulationRenderer(nn.Module):
+    """renderers.py:171-197."""
+
+    @classmethod
+    def forward(cls, weights, ray_indices=None, num_rays=None):
+        if ray_indices is not None:
+            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        return _render(weights, want_acc=True)["accumulation"]
+
+
+class DepthRenderer(nn.Module):
+    """renderers.py:200-261."""
+
+    def __init__(self, method: str = "median") -> None:
+        super().__init__()
+        if method not in ("median", "expected"):
+            raise NotImplementedError(f"Method {method} not implemented")
+        self.method = method
+
+    def forward(self, weights, ray_samples, ray_indices=None, num_rays=None):
+        if ray_indices is not None:
+            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        return _render(weights, bins=bins_of(ray_samples), depth_method=self.method)["depth"]
+
+
+class SemanticRenderer(nn.Module):
+    """renderers.py:284-295 (used as the normal renderer, base_surface_model.py:216)."""
+
+    @classmethod
+    def forward(cls, semantics, weights):
+        return _render(weights, normals=semantics, want_normal=True)["normal"]
+
+
+def render_all(weights, rgb, normals, ray_samples, background, training: bool = False, depth_method: str = "expected"):
+    """rgb + depth + normal + accumulation in one launch (what SurfaceModel.get_outputs computes with four renderers)."""
+    return _render(weights, rgb=rgb, normals=normals, bins=bins_of(ray_samples), background=background, clamp01=not training,
+                   depth_method=depth_method, want_acc=True, want_normal=True)

@@ -1,0 +1,85 @@
+"""Shared helpers for the parity tests: build the *product* SDFField for a seeded oracle case."""
+import os
+
+import numpy as np
+import torch
+
+from oracle import cases
+from oracle.field import FieldSpec, OracleField, init_params
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name, device="cpu"):
+    return {k: torch.from_numpy(v).to(device) for k, v in np.load(os.path.join(GOLDEN_DIR, name + ".npz")).items()}
+
+
+def product_field(spec: FieldSpec, params, kw, device="cuda", precision="fp32"):
+    """sdfstudio_b200.SDFField with the oracle's seeded parameters loaded (names match the reference state_dict)."""
+    import sdfstudio_b200 as sb
+
+    cfg = sb.SDFFieldConfig(
+        num_layers=spec.num_layers, hidden_dim=spec.hidden_dim, geo_feat_dim=spec.geo_feat_dim, num_layers_color=spec.num_layers_color,
+        hidden_dim_color=spec.hidden_dim_color, appearance_embedding_dim=spec.appearance_embedding_dim,
+        use_appearance_embedding=spec.use_appearance_embedding, bias=kw.get("bias", 0.5), inside_outside=kw.get("inside_outside", False),
+        use_grid_feature=spec.use_grid_feature, beta_init=kw.get("beta_init", 0.3), position_encoding_max_degree=spec.position_encoding_max_degree,
+        use_diffuse_color=spec.use_diffuse_color, use_specular_tint=spec.use_specular_tint, use_reflections=spec.use_reflections,
+        use_n_dot_v=spec.use_n_dot_v, rgb_padding=spec.rgb_padding, off_axis=spec.off_axis, use_numerical_gradients=spec.use_numerical_gradients,
+        num_levels=spec.num_levels, max_res=spec.max_res, base_res=spec.base_res, log2_hashmap_size=spec.log2_hashmap_size,
+        hash_features_per_level=spec.hash_features_per_level, hash_smoothstep=spec.hash_smoothstep, use_position_encoding=spec.use_position_encoding,
+        grid_layout=spec.grid_layout, precision=precision,
+    )  # fmt: skip
+
+    class _Contraction:  # duck-typed SceneContraction (only `.order` is read)
+        def __init__(self, order):
+            self.order = order
+
+    distortion = None
+    if spec.contraction is not None:
+        distortion = _Contraction(float("inf") if spec.contraction == "linf" else None)
+    f = sb.SDFField(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=49, spatial_distortion=distortion)
+    sd = {}
+    for k, v in params.items():
+        if k == "hash_table":
+            if spec.grid_layout == "torch":
+                sd["encoding.hash_table"] = v
+            else:
+                sd["encoding.params"] = v.reshape(-1)
+        else:
+            sd[k] = v
+    missing, unexpected = f.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(m.startswith("encoding") or m == "aabb" for m in missing), missing
+    f = f.to(device).eval()
+    if "mask_level" in kw:
+        f.update_mask(kw["mask_level"])
+    if "num_grad_delta" in kw:
+        f.set_numerical_gradients_delta(kw["num_grad_delta"])
+    return f
+
+
+def build_case(name, device="cuda", precision="fp32"):
+    spec, kw, o, d, cam, nears, fars = cases.case_inputs(name)
+    params = init_params(spec, **cases.init_kwargs(kw))
+    oracle = OracleField(spec, params)
+    if "mask_level" in kw:
+        oracle.update_mask(kw["mask_level"])
+    if "num_grad_delta" in kw:
+        oracle.numerical_gradients_delta = kw["num_grad_delta"]
+    field = product_field(spec, params, kw, device, precision)
+    return spec, kw, o, d, cam, nears, fars, oracle, field
+
+
+def make_bundle(o, d, cam, nears, fars, device="cuda"):
+    import sdfstudio_b200 as sb
+
+    R = o.shape[0]
+    return sb.RayBundle(origins=o.to(device), directions=d.to(device), pixel_area=torch.ones(R, 1, device=device),
+                        directions_norm=torch.ones(R, 1, device=device), camera_indices=cam.view(R, 1).to(device), nears=nears.to(device),
+                        fars=fars.to(device))
+
+
+def rel_err(a, b, floor=1e-3):
+    """max |a-b| / max(|b|, floor)"""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float(((a - b).abs() / b.abs().clamp_min(floor)).max())

@@ -1,0 +1,92 @@
+"""CPU-only: the C-ABI library builds/loads, exports every symbol include/sdfb200.h declares, and the ctypes struct
+mirrors have the library's sizes.  No compute calls (no GPU here)."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "sdfb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sdfb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sdfstudio_b200 import _lib
+
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/sdfb200.h but not exported"
+    # and the python binding knows each of them
+    assert set(syms) == set(_lib.EXPORTED_SYMBOLS), set(syms) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.sdfb200_version() == 100
+
+
+def test_struct_sizes_match():
+    import ctypes as C
+
+    from sdfstudio_b200 import _lib
+
+    lib = _lib.load()
+    for which, st in enumerate((_lib.GridDesc, _lib.FieldDesc, _lib.FieldParams, _lib.FieldIn, _lib.FieldOut, _lib.RenderOut)):
+        assert lib.sdfb200_struct_size(which) == C.sizeof(st)
+
+
+def test_invalid_arguments_return_error_codes_not_crashes():
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200 import _lib
+
+    lib = _lib.load()
+    g = _lib.GridDesc()
+    g.n_levels = 99  # > MAX
+    assert lib.sdfb200_grid_encode(g, None, None, 4, None, 0, None, None) == -1
+    assert b"n_levels" in lib.sdfb200_last_error_string()
+    with pytest.raises(_lib.Sdfb200Error):
+        _lib.check(lib.sdfb200_spaced_bins(None, None, None, None, 0, 4, 0, 0, None, None, None))
+    # unsupported field shapes are refused at plan time
+    d = _lib.FieldDesc()
+    assert lib.sdfb200_field_packed_bytes(d) == 0
+
+
+def test_field_descriptor_roundtrip_all_presets():
+    """packed / workspace size queries succeed for the five BASELINE config shapes (host logic only)."""
+    import torch
+
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200 import _lib
+
+    lib = _lib.load()
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    presets = {
+        "neus-facto": dict(use_grid_feature=True, num_layers=2, num_layers_color=2, log2_hashmap_size=12),
+        "volsdf": dict(num_layers=8, num_layers_color=4),
+        "angelo": dict(use_grid_feature=True, num_layers=1, num_layers_color=4, use_numerical_gradients=True, hash_features_per_level=8,
+                       hash_smoothstep=False, use_position_encoding=False, log2_hashmap_size=12, base_res=64, max_res=4096),
+        "bakedsdf": dict(use_grid_feature=True, num_layers=2, num_layers_color=2, position_encoding_max_degree=8, use_diffuse_color=True,
+                         use_specular_tint=True, use_reflections=True, use_n_dot_v=True, off_axis=True, log2_hashmap_size=12),
+    }
+    for name, kw in presets.items():
+        f = sb.SDFField(sb.SDFFieldConfig(**kw), aabb, 4)
+        d = f._field_desc()
+        assert lib.sdfb200_field_packed_bytes(d) > 0, name
+        assert lib.sdfb200_field_workspace_bytes(d, 1000) > 0, name
+    # state-dict names follow the reference
+    names = set(dict(sb.SDFField(sb.SDFFieldConfig(**presets["neus-facto"]), aabb, 4).named_parameters()))
+    for n in ("glin0.weight_g", "glin0.weight_v", "glin2.bias", "clin0.weight_v", "laplace_density.beta", "deviation_network.variance",
+              "embedding_appearance.embedding.weight", "encoding.params"):
+        assert n in names, n
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "sdfstudio_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{fn} imports oracle"
+                assert "oracle/" not in txt and "oracle." not in txt.replace("oracle.make_golden", ""), f"{fn} references oracle"

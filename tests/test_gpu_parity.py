@@ -1,0 +1,301 @@
+"""-m gpu parity tests: the CUDA path (through sdfstudio_b200's reference-shaped modules and the C-ABI) against
+(1) golden vectors minted from the unmodified reference and (2) the CPU oracle on seeded inputs.
+Tolerances: floating point outputs 1e-4 relative (BASELINE.json north_star); indices bit-exact."""
+import pytest
+import torch
+
+from oracle import cases, hashgrid, render, samplers
+from oracle.field import FieldSpec, OracleField, init_params
+
+from helpers import build_case, load_golden, make_bundle, product_field, rel_err
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4
+FIELD_CASES = list(cases.CASES)
+SAMPLER_CASES = ["neusfacto_c1", "neusfacto_c1_init", "volsdf_stock"]
+
+
+def assert_rel(a, b, tol=RTOL, floor=1e-3, what=""):
+    e = rel_err(a, b, floor)
+    assert e <= tol, f"{what}: rel err {e:.3e} > {tol:.1e}"
+
+
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["torch", "tcnn"])
+@pytest.mark.parametrize("F,smooth", [(2, True), (2, False), (8, False), (4, True), (1, False)])
+def test_grid_encode_matches_oracle(layout, F, smooth):
+    import sdfstudio_b200 as sb
+
+    L, log2T, base, maxres = 8, 12, 4, 256
+    g = hashgrid.growth_factor(L, base, maxres)
+    enc = sb.Encoding(3, {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": log2T, "base_resolution": base,
+                          "per_level_scale": g, "interpolation": "Smoothstep" if smooth else "Linear"}, layout=layout).cuda()
+    gen = torch.Generator().manual_seed(7)
+    x = torch.rand(4097, 3, generator=gen)
+    x[:8] = torch.tensor([[0, 0, 0], [1, 1, 1], [0.5, 0.25, 0.125], [1, 0, 0.5], [0.999999, 0.5, 0.5], [1e-7, 0.3, 0.9], [0.25, 0.25, 0.25], [0.75, 1, 0]])
+    table = enc.table.detach().cpu()
+    table = ((torch.rand(table.shape, generator=gen) * 2 - 1) * 0.1)
+    with torch.no_grad():
+        enc.table.copy_(table.cuda())
+    xo = x.clone().requires_grad_(True)
+    if layout == "torch":
+        scal = hashgrid.torch_layout_scalings(L, base, base * g ** (L - 1))
+        ref = hashgrid.encode_torch_layout(xo, table.view(-1, F), scal, 1 << log2T, smooth)
+    else:
+        meta = hashgrid.tcnn_grid_meta(L, F, log2T, base, g)
+        ref = hashgrid.encode_tcnn_layout(xo, table.view(-1, F), meta, F, smooth)
+    out = enc(x.cuda())
+    assert out.shape == (4097, L * F)
+    torch.testing.assert_close(out.cpu(), ref.detach(), rtol=1e-5, atol=2e-7)
+    # d out / d x through the dout_dx side output vs autograd of the oracle
+    lib = sb._lib.load()
+    o2 = torch.empty(4097, L * F, device="cuda")
+    J = torch.empty(4097, L * F, 3, device="cuda")
+    xc = x.cuda().contiguous()
+    sb._lib.check(lib.sdfb200_grid_encode(enc._desc_ref(), enc.table.data_ptr(), xc.data_ptr(), 4097, o2.data_ptr(), L * F, J.data_ptr(), 0))
+    torch.cuda.synchronize()
+    w = torch.randn(L * F, generator=gen)
+    gref = torch.autograd.grad((ref * w).sum(), xo)[0]
+    gcu = (J.cpu() * w[None, :, None]).sum(1)
+    torch.testing.assert_close(gcu[8:], gref[8:], rtol=1e-4, atol=1e-4 * float(gref.abs().max()))
+    # masked levels
+    enc.set_active_levels(5)
+    out_m = enc(x.cuda()).cpu()
+    assert torch.equal(out_m[:, : 5 * F], out.cpu()[:, : 5 * F]) and float(out_m[:, 5 * F:].abs().max()) == 0.0
+
+
+def test_grid_encode_backward_matches_autograd():
+    import sdfstudio_b200 as sb
+
+    L, F, log2T, base, maxres = 6, 2, 10, 4, 64
+    g = hashgrid.growth_factor(L, base, maxres)
+    for layout in ("torch", "tcnn"):
+        enc = sb.Encoding(3, {"n_levels": L, "n_features_per_level": F, "log2_hashmap_size": log2T, "base_resolution": base, "per_level_scale": g,
+                              "interpolation": "Smoothstep"}, layout=layout).cuda()
+        gen = torch.Generator().manual_seed(3)
+        x = torch.rand(513, 3, generator=gen)
+        table = ((torch.rand(enc.table.shape, generator=gen) * 2 - 1) * 0.1)
+        with torch.no_grad():
+            enc.table.copy_(table.cuda())
+        w = torch.randn(513, L * F, generator=gen)
+        xg = x.cuda().requires_grad_(True)
+        (enc(xg) * w.cuda()).sum().backward()
+        to = table.clone().view(-1, F).requires_grad_(True)
+        xo = x.clone().requires_grad_(True)
+        if layout == "torch":
+            ref = hashgrid.encode_torch_layout(xo, to, hashgrid.torch_layout_scalings(L, base, base * g ** (L - 1)), 1 << log2T, True)
+        else:
+            ref = hashgrid.encode_tcnn_layout(xo, to, hashgrid.tcnn_grid_meta(L, F, log2T, base, g), F, True)
+        (ref * w).sum().backward()
+        torch.testing.assert_close(enc.table.grad.cpu().view(-1, F), to.grad, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(xg.grad.cpu(), xo.grad, rtol=1e-3, atol=1e-3 * float(xo.grad.abs().max()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", FIELD_CASES)
+def test_field_matches_reference_golden(name):
+    import sdfstudio_b200 as sb
+
+    G = load_golden(name)
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name)
+    rb = make_bundle(o, d, cam, nears, fars)
+    sampler = sb.SpacedSampler(kw.get("spacing", "uniform"), num_samples=kw["S"]).eval()
+    rs = sampler(rb)
+    assert torch.equal(sb.rays.spacing_bins_of(rs).cpu(), G["spacing_bins"])  # bit-exact bin edges
+    assert torch.equal(sb.rays.bins_of(rs).cpu(), G["euclid_bins"])
+    out = field(rs, return_alphas=True, return_occupancy=True)
+    H = sb.FieldHeadNames
+    gscale = float(G["gradients"].abs().max())
+    assert_rel(out[H.SDF], G["sdf"], what="sdf")
+    assert_rel(out[H.DENSITY], G["density"], floor=1e-2, what="density")
+    assert_rel(out[H.GRADIENT], G["gradients"], floor=1e-2 * gscale, what="gradients")
+    assert_rel(out[H.NORMAL], G["normals"], floor=1e-1, what="normals")
+    assert_rel(out["points_norm"], G["points_norm"], what="points_norm")
+    assert_rel(out[H.RGB], G["rgb"], floor=1e-2, what="rgb")
+    assert_rel(out[H.ALPHA], G["alphas"], floor=1e-2, what="alpha")
+    assert_rel(out[H.OCCUPANCY], G["occupancy"], floor=1e-2, what="occupancy")
+    if "sampled_sdf" in G:
+        assert_rel(out["sampled_sdf"], G["sampled_sdf"], what="sampled_sdf")
+    assert_rel(field.get_sdf(rs), G["get_sdf"], what="get_sdf")
+    geo = field.forward_geonetwork(G["points"].cuda())
+    assert_rel(geo, G["geo_points"], floor=1e-2, what="forward_geonetwork")
+    assert_rel(field.gradient(G["points"].cuda()), G["grad_points"], floor=1e-2 * float(G["grad_points"].abs().max()), what="gradient()")
+
+
+@pytest.mark.parametrize("name", FIELD_CASES)
+def test_weights_and_renderers_match_reference_golden(name):
+    import sdfstudio_b200 as sb
+
+    G = load_golden(name, "cuda")
+    eu = G["euclid_bins"].contiguous()
+    w_a, T_a = sb.rays.weights_from_alphas(G["alphas"], True)
+    assert torch.equal(w_a, G["weights_alpha"]) and torch.equal(T_a, G["trans_alpha"])  # double-accumulated cumprod => bit-exact
+    w_d, T_d = sb.rays.weights_from_density(eu, G["density"], True)
+    torch.testing.assert_close(w_d, G["weights_density"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(T_d, G["trans_density"], rtol=1e-5, atol=1e-7)
+
+    class RS:  # minimal duck-typed RaySamples for DepthRenderer
+        _euclid_bins = eu
+
+    w = G["weights_alpha"]
+    close = lambda a, b: torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6)
+    close(sb.RGBRenderer(background_color=torch.ones(3)).eval()(G["rgb"], w), G["render_rgb_white"])
+    close(sb.RGBRenderer(background_color="last_sample").eval()(G["rgb"], w), G["render_rgb_last"])
+    close(sb.RGBRenderer(background_color=torch.ones(3)).train()(G["rgb"], G["weights_density"]), G["render_rgb_white_train"])
+    close(sb.DepthRenderer("expected")(w, RS()), G["render_depth_expected"])
+    assert torch.equal(sb.DepthRenderer("median")(w, RS()), G["render_depth_median"])
+    close(sb.AccumulationRenderer()(w), G["render_acc"])
+    close(sb.SemanticRenderer()(G["normals"], w), G["render_normal"])
+    allr = sb.render_all(w, G["rgb"], G["normals"], RS(), torch.ones(3))
+    close(allr["rgb"], G["render_rgb_white"])
+    close(allr["depth"], G["render_depth_expected"])
+    close(allr["normal"], G["render_normal"])
+    close(allr["accumulation"], G["render_acc"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SAMPLER_CASES)
+def test_pdf_and_merge_indices_bit_exact(name):
+    import sdfstudio_b200 as sb
+
+    G = load_golden(name, "cuda")
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=kw["S"]).eval()(rb)
+    new, inds = sb.PDFSampler(include_original=False, histogram_padding=0.01).eval()(rb, rs, G["pdf_weights"], num_samples=24, return_indices=True)
+    assert torch.equal(inds, G["pdf_inds"])
+    assert torch.equal(sb.rays.spacing_bins_of(new), G["pdf_spacing"])
+    assert torch.equal(sb.rays.bins_of(new), G["pdf_euclid"])
+    new2, inds2 = sb.PDFSampler(include_original=True, histogram_padding=1e-5).eval()(rb, rs, G["pdf_weights"], num_samples=16, return_indices=True)
+    assert torch.equal(inds2, G["pdf_inc_inds"])
+    assert torch.equal(sb.rays.spacing_bins_of(new2), G["pdf_inc_spacing"])
+    merged, sidx = sb.ray_samplers.merge_ray_samples(rb, rs, new)
+    assert torch.equal(sidx, G["merge_sorted_index"])
+    assert torch.equal(sb.rays.spacing_bins_of(merged), G["merge_spacing"])
+    assert torch.equal(sb.rays.bins_of(merged), G["merge_euclid"])
+
+
+@pytest.mark.parametrize("name", SAMPLER_CASES)
+def test_field_driven_samplers_match_reference_golden(name):
+    import sdfstudio_b200 as sb
+
+    G = load_golden(name, "cuda")
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs_n = sb.NeuSSampler().eval()(rb, sdf_fn=field.get_sdf)
+    torch.testing.assert_close(sb.rays.spacing_bins_of(rs_n), G["neus_spacing"], rtol=0, atol=2e-6)
+    torch.testing.assert_close(sb.rays.bins_of(rs_n), G["neus_euclid"], rtol=0, atol=8e-6)
+    rs_e = sb.ErrorBoundedSampler(num_samples=64, num_samples_eval=128, num_samples_extra=32).eval()(rb, density_fn=field.laplace_density,
+                                                                                                   sdf_fn=field.get_sdf, return_eikonal_points=False)
+    assert sb.rays.bins_of(rs_e).shape == G["eb_euclid"].shape
+    torch.testing.assert_close(sb.rays.spacing_bins_of(rs_e), G["eb_spacing"], rtol=0, atol=2e-5)
+    torch.testing.assert_close(sb.rays.bins_of(rs_e), G["eb_euclid"], rtol=0, atol=8e-5)
+    rs_u, surf = sb.UniSurfSampler().eval()(make_bundle(o, d, cam, nears, fars), occupancy_fn=field.get_occupancy, sdf_fn=field.get_sdf,
+                                            return_surface_points=True)
+    torch.testing.assert_close(sb.rays.bins_of(rs_u), G["uni_euclid"], rtol=0, atol=8e-6)
+    if G["uni_surface"].shape == surf.shape:
+        torch.testing.assert_close(surf, G["uni_surface"], rtol=1e-4, atol=1e-4)
+
+
+def test_samplers_bit_exact_vs_oracle_on_shared_inputs():
+    """Per-kernel bit-exactness: identical sdf / weights in, identical indices + bins out (config-2 sized rays)."""
+    import sdfstudio_b200 as sb
+
+    R, S = 4096, 128
+    gen = torch.Generator().manual_seed(11)
+    nears, fars = torch.full((R, 1), 0.5), torch.full((R, 1), 4.5)
+    o, d, cam = cases.synthetic_rays(R, 99)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=S).eval()(rb)
+    ob = samplers.spaced_sampler(nears, fars, S, "uniform")
+    assert torch.equal(sb.rays.bins_of(rs).cpu(), ob.euclid)
+    w = torch.rand(R, S, generator=gen) ** 6
+    w[:7] = 0.0  # all-zero weights rows (padding path)
+    new, inds = sb.PDFSampler(include_original=False, histogram_padding=1e-5).eval()(rb, rs, w.cuda()[..., None], num_samples=64, return_indices=True)
+    onew, oinds = samplers.pdf_sampler(ob, w, 64, histogram_padding=1e-5, return_indices=True)
+    mism = (inds.cpu() != oinds)
+    # the reference's torch.sum is not associative-order stable across CPUs; tolerate tie-level flips only
+    assert mism.float().mean() <= 1e-5, f"index mismatch fraction {mism.float().mean():.2e}"
+    torch.testing.assert_close(sb.rays.spacing_bins_of(new).cpu(), onew.spacing, rtol=0, atol=1e-6)
+    merged, sidx = sb.ray_samplers.merge_ray_samples(rb, rs, new)
+    om, osidx = samplers.merge_bins(ob, samplers.Bins(sb.rays.spacing_bins_of(new).cpu(), sb.rays.bins_of(new).cpu(), ob.to_euclid))
+    assert torch.equal(sidx.cpu(), osidx)
+    assert torch.equal(sb.rays.spacing_bins_of(merged).cpu(), om.spacing)
+    # NeuS fixed-inv_s weights on a shared sdf
+    sdf = (torch.rand(R, S, generator=gen) - 0.3) * torch.linspace(1, -1, S)[None]
+    wk = torch.empty(R, S, device="cuda")
+    lib = sb._lib.load()
+    eu = sb.rays.bins_of(rs)
+    sb._lib.check(lib.sdfb200_neus_upsample_weights(eu.data_ptr(), sdf.cuda().contiguous().data_ptr(), R, S, 64.0, wk.data_ptr(), 0))
+    al = samplers.neus_fixed_inv_s_alpha(ob.deltas, sdf, 64.0)
+    ow, _ = samplers.weights_from_alphas(al)
+    torch.testing.assert_close(wk.cpu()[:, :-1], ow, rtol=2e-5, atol=1e-7)
+    assert float(wk[:, -1].abs().max()) == 0.0
+
+
+# ----------------------------------------------------------------------------------------------------------------
+def test_render_pipeline_parity_config2_shape():
+    """neus-facto field (BASELINE configs[1] shape: L=16, F=2, T=2^19, MLP 2x256) on 512 rays x 128 samples:
+    rendered RGB / depth / normal within 1e-4 rel of the CPU oracle on identical rays."""
+    import sdfstudio_b200 as sb
+
+    spec = FieldSpec(num_layers=2, num_layers_color=2, hidden_dim=256, use_grid_feature=True)
+    kw = dict(bias=0.5, beta_init=0.3, perturb=0.02, hash_init_scale=0.05, seed=21)
+    params = init_params(spec, **kw)
+    oracle = OracleField(spec, params)
+    field = product_field(spec, params, kw)
+    R, S = 512, 128
+    o, d, cam = cases.synthetic_rays(R, 5)
+    nears, fars = torch.full((R, 1), 0.5), torch.full((R, 1), 4.5)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=S).eval()(rb)
+    out = field(rs, return_alphas=True)
+    H = sb.FieldHeadNames
+    w = rs.get_weights_from_alphas(out[H.ALPHA])
+    img = sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, torch.ones(3))
+    ob = samplers.spaced_sampler(nears, fars, S, "uniform")
+    oo = oracle.get_outputs(o, d, ob.starts, ob.deltas, cam, return_alphas=True)
+    ow, _ = samplers.weights_from_alphas(oo["alphas"][..., 0])
+    orgb = render.render_rgb(oo["rgb"], ow[..., None], torch.ones(3))
+    odepth = render.render_depth(ow[..., None], ob.starts[..., None], ob.ends[..., None], "expected")
+    onormal = render.render_semantics(oo["normals"], ow[..., None])
+    assert_rel(img["rgb"], orgb, floor=1e-2, what="rendered rgb")
+    assert_rel(img["depth"], odepth, floor=1e-2, what="rendered depth")
+    assert_rel(img["normal"], onormal, floor=1e-1, what="rendered normal")
+    assert_rel(out[H.SDF], oo["sdf"], what="sdf")
+
+
+def test_empty_and_ragged_inputs():
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case("neusfacto_c1_init")
+    # zero rays
+    rb0 = make_bundle(o[:0], d[:0], cam[:0], nears[:0], fars[:0])
+    rs0 = sb.UniformSampler(num_samples=8).eval()(rb0)
+    assert sb.rays.bins_of(rs0).shape == (0, 9)
+    # a ray count that is not a multiple of any tile size, 1 sample per ray
+    rb = make_bundle(o[:37], d[:37], cam[:37], nears[:37], fars[:37])
+    rs = sb.UniformSampler(num_samples=1).eval()(rb)
+    out = field(rs, return_alphas=True)
+    ob = samplers.spaced_sampler(nears[:37], fars[:37], 1, "uniform")
+    oo = oracle.get_outputs(o[:37], d[:37], ob.starts, ob.deltas, cam[:37], return_alphas=True)
+    assert_rel(out[sb.FieldHeadNames.RGB], oo["rgb"], floor=1e-2, what="rgb")
+    assert_rel(out[sb.FieldHeadNames.ALPHA], oo["alphas"], floor=1e-2, what="alpha")
+
+
+def test_large_batch_crosses_chunks():
+    """N > the internal chunk size: chunk boundaries must not show (compare a chunk-straddling slice with a small call)."""
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case("neusfacto_c1_init")
+    R, S = 1100, 64  # 70400 points > 65536
+    o, d, cam = cases.synthetic_rays(R, 123)
+    nears, fars = torch.full((R, 1), 0.5), torch.full((R, 1), 4.5)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=S).eval()(rb)
+    big = field(rs, return_alphas=True)
+    sl = slice(1000, 1050)
+    rb2 = make_bundle(o[sl], d[sl], cam[sl], nears[sl], fars[sl])
+    small = field(sb.UniformSampler(num_samples=S).eval()(rb2), return_alphas=True)
+    for k in (sb.FieldHeadNames.RGB, sb.FieldHeadNames.SDF, sb.FieldHeadNames.ALPHA, sb.FieldHeadNames.GRADIENT):
+        assert torch.equal(big[k][sl], small[k]), k
