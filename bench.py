@@ -132,10 +132,20 @@ def cpu_arm(rays_per_step, steps, warmup):
     """rays/s of the CPU oracle port on all host threads, bounded sample of the workload."""
     from sdfstudio_b200.synthetic import dtu_like_rays
 
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    ncpu = os.cpu_count() or 1
     oracle = oracle_of(make_field("cpu"))
     o, d, cam, nears, fars = dtu_like_rays(rays_per_step, 4242)
+    # torch-CPU does not scale monotonically with threads on small batches: pick the fastest thread count (<= all cores)
+    best, cores = None, ncpu
+    for t in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(t)
+        oracle_step(oracle, o, d, cam, nears, fars, S)
+        t0 = time.perf_counter()
+        oracle_step(oracle, o, d, cam, nears, fars, S)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, cores = dt, t
+    torch.set_num_threads(cores)
     for _ in range(warmup):
         oracle_step(oracle, o, d, cam, nears, fars, S)
     t0 = time.perf_counter()

@@ -246,6 +246,14 @@ int64_t sdfb200_launch_count(void);
  * verify its struct mirrors before the first call. */
 size_t sdfb200_struct_size(int32_t which);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Debug / validation hook (no reference counterpart): one CTA computes D[128,Np] = A[128,K] W[N,K]^T with the tcgen05
+ * machinery of the fused field kernel (bf16 split planes, SS- or TS-mode A operand, bulk-copy weight ring).
+ * K % 32 == 0, K <= 256, N <= 256, Np = N rounded up to 16.  scratch: >= (K/32)*planes*Np*64 bytes.
+ * ------------------------------------------------------------------------------------------------------------- */
+int sdfb200_debug_tc_gemm(const float* A, const float* W, int32_t K, int32_t N, int32_t mode_ts, int32_t planes, float* D,
+                          void* scratch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

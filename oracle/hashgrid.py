@@ -114,7 +114,8 @@ def encode_tcnn_layout(x, params, meta, n_features: int, smoothstep: bool):
     out = torch.zeros(N, L, n_features, dtype=dt)
     for l in range(L):
         scale, res, size, off, hashed = (meta[k][l] for k in ("scale", "res", "size", "offset", "hashed"))
-        pos = x * torch.tensor(scale, dtype=dt) + 0.5
+        # tiny-cuda-nn computes pos with a fused multiply-add (one rounding); emulate it through float64
+        pos = (x.double() * float(scale) + 0.5).to(dt)
         cell = torch.floor(pos)
         w = pos - cell
         cell = cell.to(torch.int64)

@@ -23,6 +23,11 @@ __constant__ float c_offaxis[3][21] = {
 
 constexpr float kHalfPi = 1.5707963267948966f;
 
+// x @ P[:, b] of the off-axis encoding -- one fixed evaluation order shared by the forward and the jacobian
+__device__ __forceinline__ float offaxis_dot(float px, float py, float pz, int b) {
+  return fmaf(pz, c_offaxis[2][b], fmaf(py, c_offaxis[1][b], px * c_offaxis[0][b]));
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // weight packing: W = v * (g / ||v||_row)   (nn.utils.weight_norm dim=0, sdf_field.py:312-313,360-361)
 // one block per output row; writes the padded [Np,Kp] matrix, its transpose [Kp,Np] and the padded bias.
@@ -124,7 +129,7 @@ __global__ void __launch_bounds__(256) k_field_inputs(const InputArgs a) {
   const int half = nb * a.pe_degree;
   for (int b = 0; b < nb; ++b) {
     float v;
-    if (a.off_axis) v = px * c_offaxis[0][b] + py * c_offaxis[1][b] + pz * c_offaxis[2][b];
+    if (a.off_axis) v = offaxis_dot(px, py, pz, b);
     else v = b == 0 ? px : (b == 1 ? py : pz);
     float fr = 1.f;
     for (int k = 0; k < a.pe_degree; ++k, fr *= 2.f) {
@@ -267,11 +272,15 @@ __global__ void __launch_bounds__(256) k_grad_finish(const GradArgs a) {
     const int nb = a.off_axis ? 21 : 3;
     const int half = nb * a.pe_degree;
     for (int b = 0; b < nb; ++b) {
+      float v;
+      if (a.off_axis) v = offaxis_dot(in[0], in[1], in[2], b);
+      else v = in[b];
       float acc = 0.f, fr = 1.f;
       for (int k = 0; k < a.pe_degree; ++k, fr *= 2.f) {
         const int c = 3 + b * a.pe_degree + k;
-        // d sin(v f)/dv = f cos(v f) = f * in[c+half];   d sin(v f + pi/2)/dv = -f sin(v f) = -f * in[c]
-        acc += fr * (g[c] * in[c + half] - g[c + half] * in[c]);
+        // autograd of sin(s) and sin(u), u = fl(s + pi/2): cos evaluated on the SAME fp32 arguments as the forward
+        const float sarg = v * fr;
+        acc += fr * (g[c] * cosf(sarg) + g[c + half] * cosf(sarg + kHalfPi));
       }
       if (a.off_axis) { gx += acc * c_offaxis[0][b]; gy += acc * c_offaxis[1][b]; gz += acc * c_offaxis[2][b]; }
       else if (b == 0) gx += acc; else if (b == 1) gy += acc; else gz += acc;

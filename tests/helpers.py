@@ -83,3 +83,43 @@ def rel_err(a, b, floor=1e-3):
     """max |a-b| / max(|b|, floor)"""
     a, b = a.detach().float().cpu(), b.detach().float().cpu()
     return float(((a - b).abs() / b.abs().clamp_min(floor)).max())
+
+
+def oracle64(spec, params, kw):
+    """float64 instance of the oracle: the 'exact' answer used to calibrate fp32 noise."""
+    o = OracleField(spec, params, dtype=torch.float64)
+    if "mask_level" in kw:
+        o.update_mask(kw["mask_level"])
+    if "num_grad_delta" in kw:
+        o.numerical_gradients_delta = kw["num_grad_delta"]
+    return o
+
+
+def assert_within_noise(cuda, ref32, ref64, what, factor=4.0, floor=2e-6):
+    """|cuda - exact| must not exceed `factor` x the reference's OWN fp32 rounding noise |ref32 - exact| (max-norm), with an
+    absolute floor.  Used where the quantity is ill-conditioned in fp32 (numerical gradients, inverse-CDF sampling), so
+    that a fixed relative bound would be either meaningless or unattainable by any fp32 implementation."""
+    cuda, ref32, ref64 = (t.detach().double().cpu() for t in (cuda, ref32, ref64))
+    noise = float((ref32 - ref64).abs().max())
+    err = float((cuda - ref64).abs().max())
+    bound = max(floor, factor * noise)
+    assert err <= bound, f"{what}: |cuda-exact| = {err:.3e} > {bound:.3e} (reference fp32 noise {noise:.3e})"
+
+
+def cdf_consistency(existing_spacing, weights, new_bins, u, hist_pad, eps=1e-5):
+    """max |cdf(new_bin) - u| evaluated in float64: the forward map of PDF sampling is well conditioned even where its
+    inverse (the bin position) is not."""
+    w = weights.double() + hist_pad
+    ws = w.sum(-1, keepdim=True)
+    pad = torch.relu(eps - ws)
+    w = w + pad / w.shape[-1]
+    ws = ws + pad
+    cdf = torch.cumsum(w / ws, -1).clamp(max=1.0)
+    cdf = torch.cat([torch.zeros_like(cdf[:, :1]), cdf], -1)
+    eb = existing_spacing.double()
+    nb = new_bins.double()
+    idx = torch.searchsorted(eb.contiguous(), nb.contiguous(), right=True).clamp(1, eb.shape[1] - 1)
+    b0, b1 = torch.gather(eb, 1, idx - 1), torch.gather(eb, 1, idx)
+    c0, c1 = torch.gather(cdf, 1, idx - 1), torch.gather(cdf, 1, idx)
+    t = ((nb - b0) / (b1 - b0).clamp_min(1e-30)).clamp(0, 1)
+    return float((c0 + t * (c1 - c0) - u.double()).abs().max())
