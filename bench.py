@@ -201,7 +201,7 @@ def main():
 
     precision = args.precision
     if precision == "auto":
-        precision = "fp32"
+        precision = "bf16x3"   # tcgen05 path at parity-grade precision (bf16 split, fp32 accumulate); fp32 / bf16 via --precision
     field = make_field(dev, precision)
     sampler = sb.UniformSampler(num_samples=S).eval()
     white = torch.ones(3, device=dev)

@@ -254,6 +254,10 @@ size_t sdfb200_struct_size(int32_t which);
 int sdfb200_debug_tc_gemm(const float* A, const float* W, int32_t K, int32_t N, int32_t mode_ts, int32_t planes, float* D,
                           void* scratch, void* stream);
 
+/* debug: copies the 16x32 clock64 phase stamps recorded by the fused tensor-core kernel when the environment variable
+ * SDFB200_TC_TIMING is set (CTA 0, first 16 tiles) into a HOST buffer of 512 int64. */
+int sdfb200_debug_tc_timing(long long* host_out_512);
+
 #ifdef __cplusplus
 }
 #endif

@@ -12,21 +12,31 @@
 //   heads    Laplace density, NeuS alpha, occupancy, normals
 // MMA = tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M=128.  bf16x3: a0*w0 + a1*w0 + a0*w1 with a = a0+a1, w = w0+w1
 // (error ~2^-16 relative, fp32 accumulate).  Weights stream through a 3-stage shared-memory ring filled by 1-D bulk
-// copies (UBLKCP) from a pre-packed image; warp 16 = producer, warp 17 = MMA issuer, warps 0-15 = encode + epilogues.
+// copies (UBLKCP) from a pre-packed image.  Warp roles: 0-15 epilogues, 16 weight producer, 17 MMA issuer.  The epilogue
+// warps encode the NEXT tile's input in seven slices, one before each wait for an MMA phase, into a double-buffered
+// smem operand -- the L2-latency-bound hash gathers run in the shadow of the tensor-core work.
 #include "field_plan.h"
 #include "grid.cuh"
 #include "tc_common.cuh"
 
+#include <stdlib.h>
+
 namespace sdfb200 {
 using namespace tc;
 
-constexpr int kTcThreads = 576;
+constexpr int kTcThreads = 576;   // 16 epilogue warps + weight producer + MMA issuer
 constexpr int kEpiThreads = 512;
 constexpr int kStages = 3;
 constexpr int kKB = 32;           // K per streamed weight block
-constexpr int kInK = 96;          // padded K of the two small-K operands (geo input, colour misc input)
 constexpr int kMaxGridDim = 32;
+constexpr int kMaxPe = 64;         // PE columns (2 * 3 * degree)
+constexpr int kInK = 96;          // padded K of the two small-K operands (geo input, colour misc input)
 constexpr float kHalfPiF = 1.5707963267948966f;
+// per-CTA scratch: softplus'(z1) fp32 [128 KB] | geo-feature planes [P x 64 KB] | 2 x encoder side buffer
+// encoder side buffer: input jacobian (PE derivative [64][128] f32 | grid [96][128] f32) | static colour operand [P][11][128][16 B]
+constexpr size_t kJRBytes = (size_t)(kMaxPe + kMaxGridDim * 3) * 128 * 4;   // input jacobian: PE [64][128] f32 | grid [32*3][128] f32
+__host__ __device__ constexpr size_t kEncBufBytes(int planes) { return kJRBytes + (size_t)planes * 11 * 2048; }
+__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 131072 + (size_t)planes * 65536 + 2 * kEncBufBytes(planes); }
 
 enum { L_G0 = 0, L_G1, L_G2, L_B1, L_B0, L_C0GF, L_C0MISC, L_C1, L_COUNT };
 
@@ -41,6 +51,7 @@ struct TcArgs {
   TcLayer layer[L_COUNT];
   int use_grid, pe_degree, use_pe, contraction, in_dim, pe_dim, grid_dim, cm_dim, app_dim, use_n_dot_v;
   int mode;  // 0: sdf only (G0, G1)   1: everything
+  int timing;
   int n_samples, has_bins, n_tiles;
   long long n_points;
   float rgb_padding, cos_anneal;
@@ -55,7 +66,8 @@ struct TcArgs {
 };
 
 // pack fp32 W (row n, column k at W[n*ldw + colmap(k)]) into bf16 split planes, K-blocked canonical layout
-__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int planes, int split, int skip,
+struct ColMap { short src[kInK]; };   // packed K index -> source column of the fp32 weight (-1 = zero); identity when unused
+__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int planes, int use_map, const ColMap map,
                           __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nblocks * Np * kKB) return;
@@ -63,8 +75,8 @@ __global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, in
   const int n = (idx / kKB) % Np;
   const int b = idx / (kKB * Np);
   const int k = b * kKB + kk;
-  const int src = k < split ? k : k + skip;
-  const float w = (n < N && k < K) ? W[(size_t)n * ldw + src] : 0.f;
+  const int src = use_map ? (k < kInK ? map.src[k] : -1) : k;
+  const float w = (n < N && k < K && src >= 0) ? W[(size_t)n * ldw + src] : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
   const size_t plane_elems = (size_t)Np * kKB;
@@ -72,6 +84,40 @@ __global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, in
   const size_t off = (size_t)(kk / 8) * (Np * 8) + (size_t)n * 8 + (kk % 8);
   out[base + off] = hi;
   if (planes > 1) out[base + plane_elems + off] = lo;
+}
+
+// debug: per-phase clock64 stamps of CTA 0's first tiles (SDFB200_TC_TIMING=1), read by sdfb200_debug_tc_timing
+__device__ long long g_tc_timing[16 * 32];
+#define TC_STAMP(k)                                                                       \
+  do {                                                                                    \
+    if (a.timing && blockIdx.x == 0 && tid == 0 && tile_no < 16) g_tc_timing[tile_no * 32 + (k)] = clock64(); \
+  } while (0)
+
+// softplus_100 and its derivative through MUFU ex2 / lg2 / rcp.  t = 100 z.  Absolute error ~1e-7 on h (the quantity
+// that feeds the next layer), i.e. at the level of fp32 rounding of the reference's own log1p(exp(.)).
+__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void softplus100_fast(float z, float& h, float& dsig) {
+  const float t = z * 100.0f;
+  const float e = fast_ex2(fminf(t, 30.0f) * 1.4426950408889634f);   // exp(t), clamped far above the threshold
+  const float u = 1.0f + e;
+  const bool lin = t > 20.0f;                                           // PyTorch's softplus threshold
+  // log1p(e): for small e, lg2(1+e) loses the low bits of e; the series e - e^2/2 is exact enough below 2^-10
+  const float l = e < 9.765625e-4f ? e * (1.0f - 0.5f * e) : fast_lg2(u) * 0.6931471805599453f;
+  h = lin ? z : l * 0.01f;
+  dsig = lin ? 1.0f : e * fast_rcp(u);
+}
+__device__ __forceinline__ float softplus100_fast_h(float z) {
+  const float t = z * 100.0f;
+  const float e = fast_ex2(fminf(t, 30.0f) * 1.4426950408889634f);
+  const float l = e < 9.765625e-4f ? e * (1.0f - 0.5f * e) : fast_lg2(1.0f + e) * 0.6931471805599453f;
+  return t > 20.0f ? z : l * 0.01f;
+}
+// softplus'(z) recovered from h = softplus(z):  1 - exp(-100 h)   (for tiny h: 100 h (1 - 50 h))
+__device__ __forceinline__ float dsoftplus_from_h_fast(float h) {
+  const float x = 100.0f * h;
+  return x < 1.953125e-3f ? x * (1.0f - 0.5f * x) : 1.0f - fast_ex2(-x * 1.4426950408889634f);
 }
 
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -86,30 +132,157 @@ __device__ __forceinline__ void store_in(uint8_t* inA, int row, int col, float v
   if (P > 1) *reinterpret_cast<__nv_bfloat16*>(inA + (kInK / 8) * 2048 + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// sample position of point p (ray r, sample s): o + d * t_start, then SceneContraction (cameras/rays.py:61-73,
+// spatial_distortions.py:66-73).  Also returns the ray direction and the bin width.
+struct PointGeom { float px, py, pz, dx, dy, dz, delta; long long ray; };
+__device__ __forceinline__ PointGeom point_geom(const TcArgs& a, long long p) {
+  PointGeom g;
+  g.dx = g.dy = g.dz = 0.f; g.delta = 0.f;
+  g.ray = a.has_bins ? p / a.n_samples : p;
+  if (a.has_bins) {
+    const int smp = (int)(p - g.ray * a.n_samples);
+    const float t0 = __ldg(a.bins + g.ray * (a.n_samples + 1) + smp);
+    g.delta = __fsub_rn(__ldg(a.bins + g.ray * (a.n_samples + 1) + smp + 1), t0);
+    g.dx = __ldg(a.directions + g.ray * 3); g.dy = __ldg(a.directions + g.ray * 3 + 1); g.dz = __ldg(a.directions + g.ray * 3 + 2);
+    g.px = __fadd_rn(__ldg(a.origins + g.ray * 3 + 0), __fmul_rn(g.dx, t0));
+    g.py = __fadd_rn(__ldg(a.origins + g.ray * 3 + 1), __fmul_rn(g.dy, t0));
+    g.pz = __fadd_rn(__ldg(a.origins + g.ray * 3 + 2), __fmul_rn(g.dz, t0));
+  } else {
+    g.px = __ldg(a.origins + p * 3); g.py = __ldg(a.origins + p * 3 + 1); g.pz = __ldg(a.origins + p * 3 + 2);
+    if (a.directions) { g.dx = __ldg(a.directions + p * 3); g.dy = __ldg(a.directions + p * 3 + 1); g.dz = __ldg(a.directions + p * 3 + 2); }
+  }
+  if (a.contraction != SDFB200_CONTRACT_NONE) {
+    const float mag = a.contraction == SDFB200_CONTRACT_LINF
+                          ? fmaxf(fabsf(g.px), fmaxf(fabsf(g.py), fabsf(g.pz)))
+                          : sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(g.px, g.px), __fmul_rn(g.py, g.py)), __fmul_rn(g.pz, g.pz)));
+    if (mag >= 1.f) {
+      const float k = __fsub_rn(2.f, __fdiv_rn(1.f, mag));
+      g.px = __fmul_rn(k, __fdiv_rn(g.px, mag)); g.py = __fmul_rn(k, __fdiv_rn(g.py, mag)); g.pz = __fmul_rn(k, __fdiv_rn(g.pz, mag));
+    }
+  }
+  return g;
+}
+
+// One slice of the NEXT tile's input encoding, executed by the 16 epilogue warps right before they wait for an MMA phase
+// (so the L2-latency-bound gathers run in the shadow of the tensor-core work).  Thread (row, q) owns levels q, q+4, ..
+//   slices 0-3: one hash level each (8 gathers, blend, jacobian)            slice 4: positional encoding (+ derivative)
+//   slice 5   : static colour-operand columns (x, dir-enc, appearance)      slice 6: x columns, zero padding, fences
+// Outputs: geo input operand (bf16 planes, smem, canonical layout) and, in the per-CTA global scratch, the per-point
+// input jacobian JR[c][3] (d input_c / d x, laid out so that EB0 reads its 24 columns as 18 coalesced float4) and the
+// static colour columns already in operand layout (staged into smem later by one bulk copy per plane).
+template <int P>
+__device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slice, int row, int q, uint8_t* inA, uint8_t* enc) {
+  if (tile >= a.n_tiles) return;
+  float* Jpe = reinterpret_cast<float*>(enc);                       // [pe column][row]     d PE_i / d x_axis(i)
+  float* Jg = Jpe + kMaxPe * 128;                                    // [grid col * 3 + d][row]
+  uint8_t* cms = enc + kJRBytes;                                    // [P][11][128][16 B]
+  const long long p_raw = (long long)tile * 128 + row;
+  const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
+  const PointGeom g = point_geom(a, p);
+  const uint64_t pol_stream = l2_policy_evict_first();
+  if (slice < 4) {
+    const int l = q + 4 * slice;
+    if (l < a.grid.n_levels && a.grid_dim > 0) {
+      float o[2] = {0.f, 0.f};
+      float dj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      if (a.use_grid && l < a.grid.active_levels) {
+        const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;
+        encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy_evict_last());
+      }
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        const int cg = l * 2 + f;
+        store_in<P>(inA, row, 3 + a.pe_dim + cg, o[f]);
+        // positions = (x + 2) / 4 (sdf_field.py:384): the 1/4 is folded into the stored jacobian
+        st_stream(Jg + (cg * 3 + 0) * 128 + row, 0.25f * dj[f][0], pol_stream);
+        st_stream(Jg + (cg * 3 + 1) * 128 + row, 0.25f * dj[f][1], pol_stream);
+        st_stream(Jg + (cg * 3 + 2) * 128 + row, 0.25f * dj[f][2], pol_stream);
+      }
+    }
+  } else if (slice == 4) {
+    const int deg = a.pe_degree, half = 3 * deg;
+    const float pc[3] = {g.px, g.py, g.pz};
+    for (int i = q; i < half; i += 4) {                   // PE: sin(x 2^k) | sin(x 2^k + pi/2)   (encodings.py:194-198)
+      const int b = i / deg, k = i - b * deg;
+      const float fr = (float)(1 << k);
+      const float sarg = pc[b] * fr;
+      float s0, c0, s1, c1;
+      sincosf(sarg, &s0, &c0);
+      sincosf(sarg + kHalfPiF, &s1, &c1);
+      store_in<P>(inA, row, 3 + i, a.use_pe ? s0 : 0.f);
+      store_in<P>(inA, row, 3 + half + i, a.use_pe ? s1 : 0.f);
+      // autograd of sin on the forward's own fp32 arguments: d/dx_b = 2^k cos(arg)
+      st_stream(Jpe + i * 128 + row, a.use_pe ? fr * c0 : 0.f, pol_stream);
+      st_stream(Jpe + (half + i) * 128 + row, a.use_pe ? fr * c1 : 0.f, pol_stream);
+    }
+  } else if (slice == 5) {
+    if (a.mode != 0) {
+      // static colour columns (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(27) | appearance | 0
+      const float pc[3] = {g.px, g.py, g.pz};
+      const float dd[3] = {g.dx, g.dy, g.dz};
+      for (int ch = q; ch < 11; ch += 4) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          float v2[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int j = ch * 8 + e2 * 2 + u;
+            float val = 0.f;
+            if (j < 3) val = pc[j];
+            else if (j < 15) { const int i = j - 3; val = sinf(dd[i >> 2] * (float)(1 << (i & 3))); }
+            else if (j < 27) { const int i = j - 15; val = sinf(dd[i >> 2] * (float)(1 << (i & 3)) + kHalfPiF); }
+            else if (j < 30) val = dd[j - 27];
+            else if (j < 30 + a.app_dim) val = a.appearance ? __ldg(a.appearance + g.ray * a.app_dim + (j - 30)) : 0.f;
+            v2[u] = val;
+          }
+          split2(v2[0], v2[1], hi[e2], lo[e2]);
+        }
+        st_stream(cms + ((size_t)ch * 128 + row) * 16, make_uint4(hi[0], hi[1], hi[2], hi[3]), pol_stream);
+        if (P > 1) st_stream(cms + (size_t)11 * 2048 + ((size_t)ch * 128 + row) * 16, make_uint4(lo[0], lo[1], lo[2], lo[3]), pol_stream);
+      }
+    }
+  } else {
+    if (q == 0) {
+      store_in<P>(inA, row, 0, g.px); store_in<P>(inA, row, 1, g.py); store_in<P>(inA, row, 2, g.pz);
+    } else if (q == 1) {
+      for (int c = a.in_dim; c < kInK; ++c) store_in<P>(inA, row, c, 0.f);
+    }
+    fence_async_smem();                                        // smem operand -> async proxy (UMMA reads it)
+    asm volatile("fence.proxy.async.global;" ::: "memory");    // scratch -> async proxy (bulk copy of the colour columns)
+  }
+}
+
 template <int P>
 __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t kInBytes = (uint32_t)P * (kInK / 8) * 2048;       // small-K operand (all planes)
-  constexpr uint32_t kJBytes = kMaxGridDim * 3 * 128 * 4;              // grid jacobian [c][d][row] fp32
+  constexpr uint32_t kInBytes = (uint32_t)P * (kInK / 8) * 2048;       // small-K operand (all planes), double buffered
   constexpr uint32_t kStageBytes = (uint32_t)P * 256 * kKB * 2;        // one weight K-block, all planes
-  uint8_t* inA = smem;
-  float* Jbuf = reinterpret_cast<float*>(smem + kInBytes);
-  uint8_t* ring = smem + kInBytes + kJBytes;
+  uint8_t* inA0 = smem;
+  uint8_t* ring = smem + 2 * kInBytes;
   float* fbuf = reinterpret_cast<float*>(ring + kStages * kStageBytes);
-  float* xbuf = fbuf;                 // [3][128]   contracted position
-  float* gradbuf = fbuf + 3 * 128;    // [3][128]
-  float* sdfbuf = fbuf + 6 * 128;     // [128]
-  float* red = fbuf + 7 * 128;        // [3][4][128] partial sums
-  __shared__ uint64_t full[kStages], empty[kStages], dfull;
+  float* red = fbuf;                  // [3][4][128] partial sums
+  float* prm = fbuf + 12 * 128;       // [9][256] biases / fp32 weight rows used by the epilogues
+  __shared__ uint64_t full[kStages], empty[kStages], dfull, cm_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&dfull, 1);
+    mbar_init(&cm_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  {
+    const char* blob = a.blob;
+    const float* src[9] = {reinterpret_cast<const float*>(blob + a.b_g0), reinterpret_cast<const float*>(blob + a.b_g1),
+                           reinterpret_cast<const float*>(blob + a.b_g2) + 1, reinterpret_cast<const float*>(blob + a.w_g2),
+                           reinterpret_cast<const float*>(blob + a.b_c0), reinterpret_cast<const float*>(blob + a.b_c1),
+                           reinterpret_cast<const float*>(blob + a.w_c2), reinterpret_cast<const float*>(blob + a.w_c2) + 256,
+                           reinterpret_cast<const float*>(blob + a.w_c2) + 512};
+    for (int i = tid; i < 9 * 256; i += kTcThreads) prm[i] = src[i >> 8][i & 255];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -139,8 +312,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
   } else if (warp == 17) {
     // ============================== MMA issuer ==============================
     uint32_t it = 0;
-    const uint32_t in_base = smem_u32(inA);
+    int tile_no = -1;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      ++tile_no;
+      const uint32_t in_base = smem_u32(inA0 + (tile_no & 1) * kInBytes);
       for (int L = 0; L < nphase_layers; ++L) {
         const bool continues = (L == L_C0MISC);           // accumulates onto C0GF, no barrier in between
         if (!continues) {
@@ -148,6 +323,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
           tc_fence_after();
         }
         if (lane == 0) {
+          if (L == L_C0MISC) { mbar_wait(&cm_full, tile_no & 1); tc_fence_after(); }
           const TcLayer ly = a.layer[L];
           const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
           const uint32_t idesc = make_idesc_bf16(128, ly.Np);
@@ -189,98 +365,65 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       }
     }
   } else {
-    // ============================== encode + epilogues (16 warps) ==============================
+    // ============================== epilogues + sliced encode of the next tile (16 warps) ==============================
     const int row = (warp & 3) * 32 + lane;               // tile row == TMEM lane
     const int q = warp >> 2;                              // column quarter
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
     const char* blob = a.blob;
-    const float* b_g0 = reinterpret_cast<const float*>(blob + a.b_g0);
-    const float* b_g1 = reinterpret_cast<const float*>(blob + a.b_g1);
-    const float* b_g2 = reinterpret_cast<const float*>(blob + a.b_g2);
-    const float* w_g2 = reinterpret_cast<const float*>(blob + a.w_g2);   // row 0 of the last geo layer
-    const float* b_c0 = reinterpret_cast<const float*>(blob + a.b_c0);
-    const float* b_c1 = reinterpret_cast<const float*>(blob + a.b_c1);
-    const float* w_c2 = reinterpret_cast<const float*>(blob + a.w_c2);   // [3 rows][256]
+    const float* p_bg0 = prm;             // smem copies (broadcast LDS.128 instead of one LDG per element)
+    const float* p_bg1 = prm + 256;
+    const float* p_bg2 = prm + 512;       // geo-feature bias (b_g2[1..])
+    const float* p_wg2 = prm + 768;       // row 0 of the last geo layer
+    const float* p_bc0 = prm + 1024;
+    const float* p_bc1 = prm + 1280;
+    const float* p_wc2 = prm + 1536;      // [3][256]
+    const float sdf_bias = __ldg(reinterpret_cast<const float*>(blob + a.b_g2));
     const float* b_c2 = reinterpret_cast<const float*>(blob + a.b_c2);
     float* sig_s = reinterpret_cast<float*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);        // [64 units][128 rows][4]
     uint8_t* gf_s = reinterpret_cast<uint8_t*>(sig_s) + 131072;                                          // [P][32 units][128][16 B]
+    uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x encoder side buffers
     uint32_t dpar = 0;
-    const int deg = a.pe_degree;
+    const uint64_t pol_stream = l2_policy_evict_first();
 
+    // prologue: encode the first tile completely
+    for (int sl = 0; sl < 7; ++sl) encode_slice<P>(a, blockIdx.x, sl, row, q, inA0, enc_s);
+
+    int tile_no = -1;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      ++tile_no;
+      TC_STAMP(0);
+      const int buf = tile_no & 1;
+      uint8_t* inA = inA0 + buf * kInBytes;               // geo input now, colour operand later
+      uint8_t* inA_next = inA0 + (buf ^ 1) * kInBytes;
+      uint8_t* enc_cur = enc_s + (size_t)buf * kEncBufBytes(P);
+      uint8_t* enc_next = enc_s + (size_t)(buf ^ 1) * kEncBufBytes(P);
+      const int next_tile = tile + gridDim.x;
       const long long p_raw = (long long)tile * 128 + row;
       const bool valid = p_raw < a.n_points;
       const long long p = valid ? p_raw : a.n_points - 1;
-      const long long ray = a.has_bins ? p / a.n_samples : p;
-      const int smp = a.has_bins ? (int)(p - ray * a.n_samples) : 0;
-      // ---------------- position (all four quarter-threads of a row compute it) ----------------
-      float px, py, pz, dirx = 0.f, diry = 0.f, dirz = 0.f, delta = 0.f;
-      if (a.has_bins) {
-        const float t0 = __ldg(a.bins + ray * (a.n_samples + 1) + smp);
-        delta = __fsub_rn(__ldg(a.bins + ray * (a.n_samples + 1) + smp + 1), t0);
-        dirx = __ldg(a.directions + ray * 3); diry = __ldg(a.directions + ray * 3 + 1); dirz = __ldg(a.directions + ray * 3 + 2);
-        px = __fadd_rn(__ldg(a.origins + ray * 3 + 0), __fmul_rn(dirx, t0));
-        py = __fadd_rn(__ldg(a.origins + ray * 3 + 1), __fmul_rn(diry, t0));
-        pz = __fadd_rn(__ldg(a.origins + ray * 3 + 2), __fmul_rn(dirz, t0));
-      } else {
-        px = __ldg(a.origins + p * 3); py = __ldg(a.origins + p * 3 + 1); pz = __ldg(a.origins + p * 3 + 2);
-        if (a.directions) { dirx = __ldg(a.directions + p * 3); diry = __ldg(a.directions + p * 3 + 1); dirz = __ldg(a.directions + p * 3 + 2); }
+      const PointGeom pg = point_geom(a, p);
+      const float px = pg.px, py = pg.py, pz = pg.pz, dirx = pg.dx, diry = pg.dy, dirz = pg.dz, delta = pg.delta;
+      if (q == 0 && valid) {
+        if (a.out.points_norm) a.out.points_norm[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+        if (a.out.points) { a.out.points[p * 3] = px; a.out.points[p * 3 + 1] = py; a.out.points[p * 3 + 2] = pz; }
       }
-      if (a.contraction != SDFB200_CONTRACT_NONE) {
-        const float mag = a.contraction == SDFB200_CONTRACT_LINF ? fmaxf(fabsf(px), fmaxf(fabsf(py), fabsf(pz)))
-                                                                  : sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
-        if (mag >= 1.f) {
-          const float k = __fsub_rn(2.f, __fdiv_rn(1.f, mag));
-          px = __fmul_rn(k, __fdiv_rn(px, mag)); py = __fmul_rn(k, __fdiv_rn(py, mag)); pz = __fmul_rn(k, __fdiv_rn(pz, mag));
-        }
-      }
-      const float pc[3] = {px, py, pz};
-      // ---------------- geo input -> inA (bf16 planes) ----------------
-      if (q == 0) {
-        store_in<P>(inA, row, 0, px); store_in<P>(inA, row, 1, py); store_in<P>(inA, row, 2, pz);
-        if (valid) {
-          if (a.out.points_norm) a.out.points_norm[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
-          if (a.out.points) { a.out.points[p * 3] = px; a.out.points[p * 3 + 1] = py; a.out.points[p * 3 + 2] = pz; }
-        }
-      }
-      if (q == 1)
-        for (int c = a.in_dim; c < kInK; ++c) store_in<P>(inA, row, c, 0.f);
-      {
-        const int half = 3 * deg;
-        for (int i = q; i < half; i += 4) {               // PE: sin(x 2^k) | sin(x 2^k + pi/2)   (encodings.py:194-198)
-          const int b = i / deg, k = i - b * deg;
-          const float sarg = pc[b] * (float)(1 << k);
-          store_in<P>(inA, row, 3 + i, a.use_pe ? sinf(sarg) : 0.f);
-          store_in<P>(inA, row, 3 + half + i, a.use_pe ? sinf(sarg + kHalfPiF) : 0.f);
-        }
-      }
-      if (a.use_grid) {
-        const float x01 = (px + 2.0f) * 0.25f, y01 = (py + 2.0f) * 0.25f, z01 = (pz + 2.0f) * 0.25f;
-        for (int l = q; l < a.grid.n_levels; l += 4) {
-          float o[2];
-          float dj[2][3];
-          if (l < a.grid.active_levels) {
-            encode_level<float, 2, true>(a.grid, a.table, l, x01, y01, z01, o, dj);
-          } else {
-            o[0] = o[1] = 0.f;
-            dj[0][0] = dj[0][1] = dj[0][2] = dj[1][0] = dj[1][1] = dj[1][2] = 0.f;
-          }
-#pragma unroll
-          for (int f = 0; f < 2; ++f) {
-            const int c = l * 2 + f;
-            store_in<P>(inA, row, 3 + a.pe_dim + c, o[f]);
-            Jbuf[(c * 3 + 0) * 128 + row] = dj[f][0]; Jbuf[(c * 3 + 1) * 128 + row] = dj[f][1]; Jbuf[(c * 3 + 2) * 128 + row] = dj[f][2];
-          }
-        }
-      } else {
-        for (int c = q; c < a.grid_dim; c += 4) store_in<P>(inA, row, 3 + a.pe_dim + c, 0.f);
-      }
-      fence_async_smem();
       tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
+      named_arrive(1, kEpiThreads + 32);                  // input operand staged (previous tile / prologue), D and A planes free
+      TC_STAMP(1);
+      encode_slice<P>(a, next_tile, 0, row, q, inA_next, enc_next);
+      if (a.mode == 0) { encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 2, row, q, inA_next, enc_next); }
 
       // ---------------- E0: h1 = softplus(z1) -> A planes ; softplus'(z1) -> scratch ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(2);
+      if (a.mode != 0 && tid == 0) {
+        // G0 has consumed the geo input: chunks 1..11 of this buffer take the static colour columns prepared one tile ago
+        // (bulk copy global scratch -> smem, completes on cm_full; C0MISC waits for it)
+        const uint8_t* cms = enc_cur + kJRBytes;
+        mbar_arrive_expect_tx(&cm_full, (uint32_t)P * 11 * 2048);
+#pragma unroll
+        for (int pl = 0; pl < P; ++pl) bulk_g2s(inA + pl * (kInK / 8) * 2048 + 2048, cms + (size_t)pl * 11 * 2048, 11 * 2048, &cm_full);
+      }
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
@@ -290,32 +433,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         uint32_t hi[8], lo[8];
         float sg[16];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float h[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float z = __uint_as_float(v[j + u]) + __ldg(b_g0 + col0 + j + u);
-            const float t = z * 100.0f;
-            const float e = expf(t);
-            h[u] = t > 20.0f ? z : log1pf(e) * 0.01f;
-            sg[j + u] = t > 20.0f ? 1.0f : __fdividef(e, 1.0f + e);
-          }
-          split2(h[0], h[1], hi[j >> 1], lo[j >> 1]);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p_bg0 + col0 + j);
+          float h0, h1, h2, h3;
+          softplus100_fast(__uint_as_float(v[j]) + b4.x, h0, sg[j]);
+          softplus100_fast(__uint_as_float(v[j + 1]) + b4.y, h1, sg[j + 1]);
+          softplus100_fast(__uint_as_float(v[j + 2]) + b4.z, h2, sg[j + 2]);
+          softplus100_fast(__uint_as_float(v[j + 3]) + b4.w, h3, sg[j + 3]);
+          split2(h0, h1, hi[j >> 1], lo[j >> 1]);
+          split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
         }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
         if (a.mode != 0) {
 #pragma unroll
           for (int u4 = 0; u4 < 4; ++u4)
-            *reinterpret_cast<float4*>(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4) = make_float4(sg[4 * u4], sg[4 * u4 + 1], sg[4 * u4 + 2], sg[4 * u4 + 3]);
+            st_stream(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4, make_float4(sg[4 * u4], sg[4 * u4 + 1], sg[4 * u4 + 2], sg[4 * u4 + 3]), pol_stream);
         }
       }
       tc_wait_st();
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(3);
+      if (a.mode == 0) { encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 6, row, q, inA_next, enc_next); }
+      else encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next);
 
       // ---------------- E1: h2 -> A planes ; sdf = W2[0,:] . h2 + b (fp32) ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(4);
       float sdf_part = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
@@ -325,16 +470,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         tc_wait_ld();
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          float h[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float z = __uint_as_float(v[j + u]) + __ldg(b_g1 + col0 + j + u);
-            const float t = z * 100.0f;
-            h[u] = t > 20.0f ? z : log1pf(expf(t)) * 0.01f;
-            sdf_part = fmaf(__ldg(w_g2 + col0 + j + u), h[u], sdf_part);
-          }
-          split2(h[0], h[1], hi[j >> 1], lo[j >> 1]);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(p_bg1 + col0 + j);
+          const float4 w4 = *reinterpret_cast<const float4*>(p_wg2 + col0 + j);
+          const float h0 = softplus100_fast_h(__uint_as_float(v[j]) + b4.x), h1 = softplus100_fast_h(__uint_as_float(v[j + 1]) + b4.y);
+          const float h2 = softplus100_fast_h(__uint_as_float(v[j + 2]) + b4.z), h3 = softplus100_fast_h(__uint_as_float(v[j + 3]) + b4.w);
+          sdf_part = fmaf(w4.x, h0, sdf_part); sdf_part = fmaf(w4.y, h1, sdf_part);
+          sdf_part = fmaf(w4.z, h2, sdf_part); sdf_part = fmaf(w4.w, h3, sdf_part);
+          split2(h0, h1, hi[j >> 1], lo[j >> 1]);
+          split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
         }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
@@ -343,16 +487,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       red[q * 128 + row] = sdf_part;
       tc_fence_before();
       if (a.mode != 0) named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(5);
       named_sync(2, kEpiThreads);
-      float sdf = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]) + __ldg(b_g2);
+      float sdf = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]) + sdf_bias;
       if (q == 0 && valid && a.out.sdf) a.out.sdf[p] = sdf;
       if (a.mode == 0) {
-        named_sync(2, kEpiThreads);  // `red` is reused by the next tile
+        named_sync(2, kEpiThreads);  // `red` is reused by the next tile; also orders the next tile's staged input
         continue;
       }
+      encode_slice<P>(a, next_tile, 2, row, q, inA_next, enc_next);
 
       // ---------------- E2: geo feature -> scratch planes ; g2 = W2[0,:] * softplus'(z2) -> A planes ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(6);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
@@ -362,16 +509,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 2) {
-          const float g0 = __uint_as_float(v[j]) + __ldg(b_g2 + 1 + col0 + j);
-          const float g1 = __uint_as_float(v[j + 1]) + __ldg(b_g2 + 1 + col0 + j + 1);
+          const float2 b2 = *reinterpret_cast<const float2*>(p_bg2 + col0 + j);
+          const float g0 = __uint_as_float(v[j]) + b2.x;
+          const float g1 = __uint_as_float(v[j + 1]) + b2.y;
           if (a.out.geo_feature && valid) { a.out.geo_feature[p * 256 + col0 + j] = g0; a.out.geo_feature[p * 256 + col0 + j + 1] = g1; }
           split2(g0, g1, hi[j >> 1], lo[j >> 1]);
         }
 #pragma unroll
         for (int u8 = 0; u8 < 2; ++u8) {
           const size_t unit = ((size_t)((col0 >> 3) + u8) * 128 + row) * 16;
-          *reinterpret_cast<uint4*>(gf_s + unit) = make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]);
-          if (P > 1) *reinterpret_cast<uint4*>(gf_s + 65536 + unit) = make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]);
+          st_stream(gf_s + unit, make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]), pol_stream);
+          if (P > 1) st_stream(gf_s + 65536 + unit, make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]), pol_stream);
         }
         // h2 (A planes) -> g2 in place.  softplus'(z) = 1 - exp(-100 h)
         uint32_t h_hi[8], h_lo[8];
@@ -382,8 +530,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         for (int j = 0; j < 8; ++j) {
           float ha = bf16lo_to_f32(h_hi[j]), hb = bf16hi_to_f32(h_hi[j]);
           if (P > 1) { ha += bf16lo_to_f32(h_lo[j]); hb += bf16hi_to_f32(h_lo[j]); }
-          const float ga = __ldg(w_g2 + col0 + 2 * j) * -expm1f(-100.0f * ha);
-          const float gb = __ldg(w_g2 + col0 + 2 * j + 1) * -expm1f(-100.0f * hb);
+          const float2 w2 = *reinterpret_cast<const float2*>(p_wg2 + col0 + 2 * j);
+          const float ga = w2.x * dsoftplus_from_h_fast(ha);
+          const float gb = w2.y * dsoftplus_from_h_fast(hb);
           split2(ga, gb, hi[j], lo[j]);
         }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
@@ -392,21 +541,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       tc_wait_st();
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(7);
+      encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next);
 
       // ---------------- EB1: g1 = (W1^T g2) * softplus'(z1) -> A planes ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
-#pragma unroll 1
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(8);
+#pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
+        float4 s4[4];
+#pragma unroll
+        for (int u4 = 0; u4 < 4; ++u4) s4[u4] = ld_stream_f4(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4, pol_stream);
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int u4 = 0; u4 < 4; ++u4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4);
-          split2(__uint_as_float(v[4 * u4]) * s4.x, __uint_as_float(v[4 * u4 + 1]) * s4.y, hi[2 * u4], lo[2 * u4]);
-          split2(__uint_as_float(v[4 * u4 + 2]) * s4.z, __uint_as_float(v[4 * u4 + 3]) * s4.w, hi[2 * u4 + 1], lo[2 * u4 + 1]);
+          split2(__uint_as_float(v[4 * u4]) * s4[u4].x, __uint_as_float(v[4 * u4 + 1]) * s4[u4].y, hi[2 * u4], lo[2 * u4]);
+          split2(__uint_as_float(v[4 * u4 + 2]) * s4[u4].z, __uint_as_float(v[4 * u4 + 3]) * s4[u4].w, hi[2 * u4 + 1], lo[2 * u4 + 1]);
         }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
@@ -414,47 +568,80 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       tc_wait_st();
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(9);
+      encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next);
 
-      // ---------------- EB0: gin (96 cols) -> d sdf / dx ; colour misc input ; reload geo feature ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      // ---------------- EB0: gin (96 cols) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ; geo feature reload
+      // the jacobian units and the geo-feature planes do not depend on this phase's MMA: fetch them before waiting
+      // thread (row, q) owns input columns [24 q, 24 q + 24); per column: x -> identity, PE -> one factor on its axis,
+      // grid -> 3 factors, padding -> 0.  Column classes are warp-uniform (q is), so there is no divergence.
+      const float* Jpe = reinterpret_cast<const float*>(enc_cur);
+      const float* Jg = Jpe + kMaxPe * 128;
+      const int deg = a.pe_degree, half = 3 * deg;
+      auto load_jac = [&](int c0, float (&jf)[24]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = c0 + j;
+          float jx = 0.f, jy = 0.f, jz = 0.f;
+          if (c < 3) {
+            jx = c == 0 ? 1.f : 0.f; jy = c == 1 ? 1.f : 0.f; jz = c == 2 ? 1.f : 0.f;
+          } else if (c < 3 + a.pe_dim) {
+            int i = c - 3;
+            const float dv = ld_stream_f1(Jpe + i * 128 + row, pol_stream);
+            if (i >= half) i -= half;
+            jx = i < deg ? dv : 0.f; jy = (i >= deg && i < 2 * deg) ? dv : 0.f; jz = i >= 2 * deg ? dv : 0.f;
+          } else if (c < a.in_dim) {
+            const int cg = c - 3 - a.pe_dim;
+            jx = ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_stream);
+            jy = ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_stream);
+            jz = ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_stream);
+          }
+          jf[3 * j] = jx; jf[3 * j + 1] = jy; jf[3 * j + 2] = jz;
+        }
+      };
+      float jf0[24];
+      load_jac(q * 24, jf0);                              // independent of this phase's MMA: fetch before waiting
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(10);
       {
         float gx = 0.f, gy = 0.f, gz = 0.f;
-        const int half = 3 * deg;
-#pragma unroll 1
+#pragma unroll
         for (int c8 = 0; c8 < 3; ++c8) {
-          const int c0 = q * 24 + c8 * 8;
           uint32_t v[8];
-          tmem_ld8(d_tmem + lane_addr + c0, v);
+          tmem_ld8(d_tmem + lane_addr + q * 24 + c8 * 8, v);
+          float jf1[24];
+          if (c8 < 2) load_jac(q * 24 + (c8 + 1) * 8, jf1);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const int c = c0 + j;
             const float g = __uint_as_float(v[j]);
-            if (c < 3) {
-              if (c == 0) gx += g; else if (c == 1) gy += g; else gz += g;
-            } else if (c < 3 + a.pe_dim) {
-              if (a.use_pe) {
-                int i = c - 3;
-                const bool second = i >= half;
-                if (second) i -= half;
-                const int b = i / deg, k = i - b * deg;
-                const float fr = (float)(1 << k);
-                const float sarg = pc[b] * fr;
-                const float dv = fr * g * cosf(second ? sarg + kHalfPiF : sarg);   // autograd of sin on the forward's fp32 argument
-                if (b == 0) gx += dv; else if (b == 1) gy += dv; else gz += dv;
-              }
-            } else if (c < a.in_dim) {
-              if (a.use_grid) {
-                const int cg = c - 3 - a.pe_dim;
-                const float g4 = 0.25f * g;                                        // positions = (x + 2) / 4
-                gx = fmaf(g4, Jbuf[(cg * 3 + 0) * 128 + row], gx);
-                gy = fmaf(g4, Jbuf[(cg * 3 + 1) * 128 + row], gy);
-                gz = fmaf(g4, Jbuf[(cg * 3 + 2) * 128 + row], gz);
-              }
-            }
+            gx = fmaf(g, jf0[3 * j], gx); gy = fmaf(g, jf0[3 * j + 1], gy); gz = fmaf(g, jf0[3 * j + 2], gz);
+          }
+          if (c8 < 2) {
+#pragma unroll
+            for (int j = 0; j < 24; ++j) jf0[j] = jf1[j];
           }
         }
         red[(0 * 4 + q) * 128 + row] = gx; red[(1 * 4 + q) * 128 + row] = gy; red[(2 * 4 + q) * 128 + row] = gz;
+      }
+      // geo feature planes back into the A operand (all L2 loads in flight before the first TMEM store)
+      {
+        uint4 gh[8], gl[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const size_t unit = ((size_t)(q * 8 + u) * 128 + row) * 16;
+          gh[u] = ld_stream_u4(gf_s + unit, pol_stream);
+          if (P > 1) gl[u] = ld_stream_u4(gf_s + 65536 + unit, pol_stream);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u += 2) {
+          const uint32_t h8[8] = {gh[u].x, gh[u].y, gh[u].z, gh[u].w, gh[u + 1].x, gh[u + 1].y, gh[u + 1].z, gh[u + 1].w};
+          tmem_st8(a_tmem + lane_addr + (q * 8 + u) * 4, h8);
+          if (P > 1) {
+            const uint32_t l8[8] = {gl[u].x, gl[u].y, gl[u].z, gl[u].w, gl[u + 1].x, gl[u + 1].y, gl[u + 1].z, gl[u + 1].w};
+            tmem_st8(a_tmem + 128 + lane_addr + (q * 8 + u) * 4, l8);
+          }
+        }
       }
       named_sync(2, kEpiThreads);
       const float grx = (red[(0 * 4 + 0) * 128 + row] + red[(0 * 4 + 1) * 128 + row]) + (red[(0 * 4 + 2) * 128 + row] + red[(0 * 4 + 3) * 128 + row]);
@@ -462,42 +649,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       const float grz = (red[(2 * 4 + 0) * 128 + row] + red[(2 * 4 + 1) * 128 + row]) + (red[(2 * 4 + 2) * 128 + row] + red[(2 * 4 + 3) * 128 + row]);
       const float gn = fmaxf(sqrtf(grx * grx + gry * gry + grz * grz), 1e-12f);      // F.normalize eps
       const float nx = grx / gn, ny = gry / gn, nz = grz / gn;
-      // colour misc input [x(3) | dir-enc(27) | grad(3) | appearance | n.v | 0...]   (sdf_field.py:572-584)
-#pragma unroll 1
-      for (int j = 0; j < 24; ++j) {
-        const int c = q * 24 + j;
-        float val = 0.f;
-        if (c < 3) val = pc[c];
-        else if (c < 30) {
-          const int i = c - 3;
-          const float dd[3] = {dirx, diry, dirz};
-          if (i < 12) { const int b = i >> 2, k = i & 3; val = sinf(dd[b] * (float)(1 << k)); }
-          else if (i < 24) { const int b = (i - 12) >> 2, k = (i - 12) & 3; val = sinf(dd[b] * (float)(1 << k) + kHalfPiF); }
-          else val = dd[i - 24];
-        } else if (c < 33) val = c == 30 ? grx : (c == 31 ? gry : grz);
-        else if (c < 33 + a.app_dim) val = a.appearance ? __ldg(a.appearance + ray * a.app_dim + (c - 33)) : 0.f;
-        else if (a.use_n_dot_v && c == 33 + a.app_dim) val = nx * dirx + ny * diry + nz * dirz;
-        store_in<P>(inA, row, c, val);
-      }
-      // geo feature planes back into the A operand
-#pragma unroll 1
-      for (int u = 0; u < 8; ++u) {
-        const size_t unit = ((size_t)(q * 8 + u) * 128 + row) * 16;
-        const uint4 h4 = *reinterpret_cast<const uint4*>(gf_s + unit);
-        const uint32_t hh[4] = {h4.x, h4.y, h4.z, h4.w};
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_tmem + lane_addr + (q * 8 + u) * 4), "r"(hh[0]), "r"(hh[1]), "r"(hh[2]), "r"(hh[3]) : "memory");
-        if (P > 1) {
-          const uint4 l4 = *reinterpret_cast<const uint4*>(gf_s + 65536 + unit);
-          asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_tmem + 128 + lane_addr + (q * 8 + u) * 4), "r"(l4.x), "r"(l4.y), "r"(l4.z), "r"(l4.w) : "memory");
-        }
+      if (q == 0) {
+        // chunk 0 of the colour operand: [grad(3), n.v, 0, 0, 0, 0]   (sdf_field.py:572-584; columns re-ordered at pack time)
+        uint32_t hi[4], lo[4];
+        split2(grx, gry, hi[0], lo[0]);
+        split2(grz, a.use_n_dot_v ? nx * dirx + ny * diry + nz * dirz : 0.f, hi[1], lo[1]);
+        hi[2] = hi[3] = lo[2] = lo[3] = 0u;
+        *reinterpret_cast<uint4*>(inA + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
       tc_wait_st();
       fence_async_smem();
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(11);
+      encode_slice<P>(a, next_tile, 5, row, q, inA_next, enc_next);
 
       // ---------------- EC0: relu -> A planes ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(12);
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
@@ -506,17 +676,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         tc_wait_ld();
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int j = 0; j < 16; j += 2)
-          split2(fmaxf(__uint_as_float(v[j]) + __ldg(b_c0 + col0 + j), 0.f), fmaxf(__uint_as_float(v[j + 1]) + __ldg(b_c0 + col0 + j + 1), 0.f), hi[j >> 1], lo[j >> 1]);
+        for (int j = 0; j < 16; j += 2) {
+          const float2 b2 = *reinterpret_cast<const float2*>(p_bc0 + col0 + j);
+          split2(fmaxf(__uint_as_float(v[j]) + b2.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b2.y, 0.f), hi[j >> 1], lo[j >> 1]);
+        }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
       }
       tc_wait_st();
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
+      TC_STAMP(13);
+      encode_slice<P>(a, next_tile, 6, row, q, inA_next, enc_next);
 
       // ---------------- EC1: relu, last colour layer (256 -> 3) as fp32 dots ----------------
-      mbar_wait(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      TC_STAMP(14);
       {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
@@ -527,10 +702,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float c1 = fmaxf(__uint_as_float(v[j]) + __ldg(b_c1 + col0 + j), 0.f);
-            r0 = fmaf(__ldg(w_c2 + col0 + j), c1, r0);
-            r1 = fmaf(__ldg(w_c2 + 256 + col0 + j), c1, r1);
-            r2 = fmaf(__ldg(w_c2 + 512 + col0 + j), c1, r2);
+            const float c1 = fmaxf(__uint_as_float(v[j]) + p_bc1[col0 + j], 0.f);
+            r0 = fmaf(p_wc2[col0 + j], c1, r0);
+            r1 = fmaf(p_wc2[256 + col0 + j], c1, r1);
+            r2 = fmaf(p_wc2[512 + col0 + j], c1, r2);
           }
         }
         named_sync(2, kEpiThreads);   // everyone has consumed the gradient partials in `red`
@@ -563,7 +738,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
           a.out.alpha[p] = fminf(fmaxf((prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f), 0.f), 1.f);
         }
       }
-      named_sync(2, kEpiThreads);     // `red` / inA / Jbuf are rewritten by the next tile
+      named_sync(2, kEpiThreads);     // `red` is rewritten by the next tile; orders the staged input / scratch of the next tile
+      TC_STAMP(15);
     }
     tc_fence_before();
   }
@@ -603,10 +779,10 @@ bool field_tc_supported(const sdfb200_field_t& f, const FieldPlan& p) {
   if (p.n_geo != 3 || p.n_col != 3) return false;
   if (p.geo[0].N != 256 || p.geo[1].N != 256 || p.geo_feat != 256 || p.col[0].N != 256 || p.col[1].N != 256) return false;
   if (f.use_numerical_gradients || f.off_axis || f.use_diffuse_color || f.use_specular_tint || f.use_reflections) return false;
-  if (p.in_dim > kInK || p.grid_dim > kMaxGridDim) return false;
+  if (p.in_dim > kInK || p.grid_dim > kMaxGridDim || p.pe_dim > kMaxPe) return false;
   if (f.use_grid_feature && (f.grid.n_features != 2 || f.grid.table_dtype != SDFB200_DT_F32)) return false;
   const int cm = 3 + 27 + 3 + f.appearance_dim + (f.use_n_dot_v ? 1 : 0);
-  if (cm > kInK) return false;
+  if (38 + f.appearance_dim > kInK) return false;
   return true;
 }
 
@@ -616,7 +792,7 @@ size_t field_tc_packed_bytes(const sdfb200_field_t& f, const FieldPlan& p) {
   return t.total;
 }
 
-constexpr size_t kScratchPerCta(int planes) { return 131072 + (size_t)planes * 65536; }
+
 
 size_t field_tc_workspace_floats(const sdfb200_field_t& f, const FieldPlan&, int64_t) {
   const int planes = f.precision == SDFB200_PRECISION_BF16X3 ? 2 : 1;
@@ -626,25 +802,34 @@ size_t field_tc_workspace_floats(const sdfb200_field_t& f, const FieldPlan&, int
 int field_tc_pack(const sdfb200_field_t& f, const FieldPlan& p, char* blob, cudaStream_t st) {
   TcPlan t;
   make_tc_plan(f, p, t);
-  auto pack = [&](int L, const float* W, int ldw, int N, int K, int split, int skip) -> int {
+  ColMap ident;
+  for (int i = 0; i < kInK; ++i) ident.src[i] = (short)i;
+  auto pack = [&](int L, const float* W, int ldw, int N, int K, const ColMap* map) -> int {
     const TcLayer& ly = t.layer[L];
     const int tot = ly.nkb * ly.Np * kKB;
-    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, t.planes, split, skip, (__nv_bfloat16*)(blob + ly.w_off));
+    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, t.planes, map != nullptr, map ? *map : ident, (__nv_bfloat16*)(blob + ly.w_off));
     SDFB_LAUNCHED("k_tc_pack");
     return 0;
   };
   const LayerPlan &g0 = p.geo[0], &g1 = p.geo[1], &g2 = p.geo[2], &c0 = p.col[0], &c1 = p.col[1];
-  const int big = 1 << 30;
   int r;
-  if ((r = pack(L_G0, (const float*)(blob + g0.w_off), g0.Kp, 256, g0.K, big, 0))) return r;
-  if ((r = pack(L_G1, (const float*)(blob + g1.w_off), g1.Kp, 256, 256, big, 0))) return r;
-  if ((r = pack(L_G2, (const float*)(blob + g2.w_off) + g2.Kp, g2.Kp, 256, 256, big, 0))) return r;      // rows 1..256 (geo feature)
-  if ((r = pack(L_B1, (const float*)(blob + g1.wt_off), g1.Np, 256, 256, big, 0))) return r;              // W1^T: [in][out]
-  if ((r = pack(L_B0, (const float*)(blob + g0.wt_off), g0.Np, g0.K, 256, big, 0))) return r;             // W0^T: rows = input index
-  // colour layer 0: input = [x(3) dir(27) grad(3) | geo feature(256) | appearance (+ n.v)]
-  if ((r = pack(L_C0GF, (const float*)(blob + c0.w_off) + 33, c0.Kp, 256, 256, big, 0))) return r;
-  if ((r = pack(L_C0MISC, (const float*)(blob + c0.w_off), c0.Kp, 256, c0.K - 256, 33, 256))) return r;
-  if ((r = pack(L_C1, (const float*)(blob + c1.w_off), c1.Kp, 256, 256, big, 0))) return r;
+  if ((r = pack(L_G0, (const float*)(blob + g0.w_off), g0.Kp, 256, g0.K, nullptr))) return r;
+  if ((r = pack(L_G1, (const float*)(blob + g1.w_off), g1.Kp, 256, 256, nullptr))) return r;
+  if ((r = pack(L_G2, (const float*)(blob + g2.w_off) + g2.Kp, g2.Kp, 256, 256, nullptr))) return r;      // rows 1..256 (geo feature)
+  if ((r = pack(L_B1, (const float*)(blob + g1.wt_off), g1.Np, 256, 256, nullptr))) return r;              // W1^T: [in][out]
+  if ((r = pack(L_B0, (const float*)(blob + g0.wt_off), g0.Np, g0.K, 256, nullptr))) return r;             // W0^T: rows = input index
+  // colour layer 0 (sdf_field.py:572-584): reference input = [x(3) dir(27) grad(3) | geo feature(256) | appearance | n.v]
+  if ((r = pack(L_C0GF, (const float*)(blob + c0.w_off) + 33, c0.Kp, 256, 256, nullptr))) return r;
+  // misc operand, kernel order: chunk 0 = [grad(3), n.v, 0 x4] (written per tile by the epilogue), then the static part
+  // [x(3), dir-enc(27), appearance] prepared by the encoder warps
+  ColMap cm;
+  for (int i = 0; i < kInK; ++i) cm.src[i] = -1;
+  cm.src[0] = 30; cm.src[1] = 31; cm.src[2] = 32;
+  if (f.use_n_dot_v) cm.src[3] = (short)(289 + f.appearance_dim);
+  for (int i = 0; i < 30; ++i) cm.src[8 + i] = (short)i;
+  for (int i = 0; i < f.appearance_dim; ++i) cm.src[38 + i] = (short)(289 + i);
+  if ((r = pack(L_C0MISC, (const float*)(blob + c0.w_off), c0.Kp, 256, kInK, &cm))) return r;
+  if ((r = pack(L_C1, (const float*)(blob + c1.w_off), c1.Kp, 256, 256, nullptr))) return r;
   return 0;
 }
 
@@ -670,6 +855,7 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   a.contraction = in.apply_contraction ? f.contraction : SDFB200_CONTRACT_NONE;
   a.in_dim = p.in_dim; a.pe_dim = p.pe_dim; a.grid_dim = p.grid_dim; a.cm_dim = t.cm_dim; a.app_dim = f.appearance_dim; a.use_n_dot_v = f.use_n_dot_v;
   a.mode = sdf_only ? 0 : 1;
+  a.timing = getenv("SDFB200_TC_TIMING") != nullptr;
   a.n_samples = in.n_samples; a.has_bins = in.bins != nullptr; a.n_points = N; a.n_tiles = (int)ceil_div(N, 128);
   a.rgb_padding = f.rgb_padding; a.cos_anneal = in.cos_anneal_ratio;
   a.origins = in.origins; a.directions = in.directions; a.bins = in.bins; a.appearance = in.appearance; a.variance = in.variance; a.beta = in.beta;
@@ -678,7 +864,7 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   a.b_c0 = p.col[0].b_off; a.b_c1 = p.col[1].b_off; a.w_c2 = p.col[2].w_off; a.b_c2 = p.col[2].b_off;
   a.scratch = reinterpret_cast<char*>(ws); a.scratch_per_cta = per_cta; a.out = out;
   const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-  const size_t smem = (size_t)t.planes * (kInK / 8) * 2048 + kMaxGridDim * 3 * 128 * 4 + (size_t)kStages * t.planes * 256 * kKB * 2 + (7 + 12) * 128 * 4 + 1024;
+  const size_t smem = 2 * (size_t)t.planes * (kInK / 8) * 2048 + (size_t)kStages * t.planes * 256 * kKB * 2 + 12 * 128 * 4 + 9 * 256 * 4 + 1024;
   if (t.planes == 2) {
     SDFB_CUDA(cudaFuncSetAttribute(k_field_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_field_tc<2><<<grid, kTcThreads, smem, st>>>(a);
@@ -691,3 +877,8 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
 }
 
 }  // namespace sdfb200
+
+extern "C" int sdfb200_debug_tc_timing(long long* host_out_512) {
+  SDFB_CUDA(cudaMemcpyFromSymbol(host_out_512, sdfb200::g_tc_timing, sizeof(long long) * 512));
+  return 0;
+}

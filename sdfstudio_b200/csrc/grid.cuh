@@ -61,13 +61,34 @@ struct TableLoad<__half, F> {
   }
 };
 
+// L2 eviction-priority policies (createpolicy): the hash table is re-read by every tile -> evict_last; streaming
+// scratch of the fused kernel -> evict_first, so that it does not push the table out of the 126 MB L2.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+// thread-local policy used by TableLoad when the caller opted in (0 = plain loads)
+struct TablePolicy { uint64_t pol; };
+template <int F>
+__device__ __forceinline__ void table_load_f32_hint(const void* table, uint64_t row, float (&v)[F], uint64_t pol) {
+  static_assert(F == 2, "hinted loads are only used by the F=2 fused kernel");
+  const float* p = reinterpret_cast<const float*>(table) + row * F;
+  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v[0]), "=f"(v[1]) : "l"(p), "l"(pol));
+}
+
 // -----------------------------------------------------------------------------------------------------------------
 // torch layout.  out[f] and (optionally) dout[f][c] = d out[f] / d x01[c].
 // Rounding follows the reference expression tree (no FMA contraction on the value path).
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T, int F, bool GRAD>
+template <typename T, int F, bool GRAD, bool HINT = false>
 __device__ __forceinline__ void encode_level_torch(const sdfb200_grid_t& g, const void* table, int l, float x, float y, float z,
-                                                   float (&out)[F], float (&dout)[F][3]) {
+                                                   float (&out)[F], float (&dout)[F][3], uint64_t pol = 0) {
   const float s = g.scale[l];
   const float sx = __fmul_rn(x, s), sy = __fmul_rn(y, s), sz = __fmul_rn(z, s);
   const float fxf = floorf(sx), fyf = floorf(sy), fzf = floorf(sz);
@@ -88,14 +109,14 @@ __device__ __forceinline__ void encode_level_torch(const sdfb200_grid_t& g, cons
   // hash = x ^ y*P1 ^ z*P2 (int64 in the reference; the low log2T bits equal the uint32 product's low bits)
   const uint32_t hyc = cy * kPrimeY, hyf = fy * kPrimeY, hzc = cz * kPrimeZ, hzf = fz * kPrimeZ;
   float f0[F], f1[F], f2[F], f3[F], f4[F], f5[F], f6[F], f7[F];
-  TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzc) & mask), f0);  // (c,c,c)
-  TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzc) & mask), f1);  // (c,f,c)
-  TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzc) & mask), f2);  // (f,f,c)
-  TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzc) & mask), f3);  // (f,c,c)
-  TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzf) & mask), f4);  // (c,c,f)
-  TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzf) & mask), f5);  // (c,f,f)
-  TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzf) & mask), f6);  // (f,f,f)
-  TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzf) & mask), f7);  // (f,c,f)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyc ^ hzc) & mask), f0, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzc) & mask), f0);  // (c,c,c)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyf ^ hzc) & mask), f1, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzc) & mask), f1);  // (c,f,c)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyf ^ hzc) & mask), f2, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzc) & mask), f2);  // (f,f,c)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyc ^ hzc) & mask), f3, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzc) & mask), f3);  // (f,c,c)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyc ^ hzf) & mask), f4, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzf) & mask), f4);  // (c,c,f)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyf ^ hzf) & mask), f5, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzf) & mask), f5);  // (c,f,f)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyf ^ hzf) & mask), f6, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzf) & mask), f6);  // (f,f,f)
+  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyc ^ hzf) & mask), f7, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzf) & mask), f7);  // (f,c,f)
   const float nx = __fsub_rn(1.f, ox), ny = __fsub_rn(1.f, oy), nz = __fsub_rn(1.f, oz);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
@@ -118,9 +139,9 @@ __device__ __forceinline__ void encode_level_torch(const sdfb200_grid_t& g, cons
 // -----------------------------------------------------------------------------------------------------------------
 // tcnn layout
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T, int F, bool GRAD>
+template <typename T, int F, bool GRAD, bool HINT = false>
 __device__ __forceinline__ void encode_level_tcnn(const sdfb200_grid_t& g, const void* table, int l, float x, float y, float z,
-                                                  float (&out)[F], float (&dout)[F][3]) {
+                                                  float (&out)[F], float (&dout)[F][3], uint64_t pol = 0) {
   const float s = g.scale[l];
   const uint32_t res = g.resolution[l], size = g.size[l];
   const bool hashed = g.hashed[l];
@@ -153,7 +174,7 @@ __device__ __forceinline__ void encode_level_tcnn(const sdfb200_grid_t& g, const
     uint32_t idx = hashed ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
     idx %= size;
     float v[F];
-    TableLoad<T, F>::load(table, base + idx, v);
+    if constexpr (HINT) table_load_f32_hint<F>(table, base + idx, v, pol); else TableLoad<T, F>::load(table, base + idx, v);
     const float wt = wx * wy * wz;
 #pragma unroll
     for (int f = 0; f < F; ++f) {
@@ -173,13 +194,13 @@ __device__ __forceinline__ void encode_level_tcnn(const sdfb200_grid_t& g, const
   }
 }
 
-template <typename T, int F, bool GRAD>
+template <typename T, int F, bool GRAD, bool HINT = false>
 __device__ __forceinline__ void encode_level(const sdfb200_grid_t& g, const void* table, int l, float x, float y, float z,
-                                             float (&out)[F], float (&dout)[F][3]) {
+                                             float (&out)[F], float (&dout)[F][3], uint64_t pol = 0) {
   if (g.layout == SDFB200_GRID_TORCH)
-    encode_level_torch<T, F, GRAD>(g, table, l, x, y, z, out, dout);
+    encode_level_torch<T, F, GRAD, HINT>(g, table, l, x, y, z, out, dout, pol);
   else
-    encode_level_tcnn<T, F, GRAD>(g, table, l, x, y, z, out, dout);
+    encode_level_tcnn<T, F, GRAD, HINT>(g, table, l, x, y, z, out, dout, pol);
 }
 
 }  // namespace sdfb200

@@ -271,7 +271,7 @@ def test_samplers_bit_exact_vs_oracle_on_shared_inputs():
     sb._lib.check(lib.sdfb200_neus_upsample_weights(eu.data_ptr(), sdf.cuda().contiguous().data_ptr(), R, S, 64.0, wk.data_ptr(), 0))
     al = samplers.neus_fixed_inv_s_alpha(ob.deltas, sdf, 64.0)
     ow, _ = samplers.weights_from_alphas(al)
-    torch.testing.assert_close(wk.cpu()[:, :-1], ow, rtol=2e-5, atol=1e-7)
+    torch.testing.assert_close(wk.cpu()[:, :-1], ow, rtol=2e-5, atol=5e-7)
     assert float(wk[:, -1].abs().max()) == 0.0
 
 

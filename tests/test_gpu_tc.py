@@ -29,3 +29,86 @@ def test_tc_gemm_tile(ts, planes, K, N):
     if planes == 2:
         # the split must actually buy precision: error well below a single bf16 pass
         assert err < 1e-4
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# fused tensor-core field kernel (k_field_tc): bf16x3 must sit at the fp32 reference's own noise level, bf16 is the
+# fast mode reported with PSNR
+# ----------------------------------------------------------------------------------------------------------------
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from helpers import assert_within_noise, build_case, load_golden, make_bundle, oracle64, rel_err  # noqa: E402
+from oracle import render, samplers  # noqa: E402
+
+
+def _run_case(name, precision):
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name, precision=precision)
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=kw["S"]).eval()(rb)
+    out = field(rs, return_alphas=True, return_occupancy=True)
+    torch.cuda.synchronize()
+    eu = sb.rays.bins_of(rs).cpu().double()
+    o64 = oracle64(spec, oracle.p, kw)
+    e64 = o64.get_outputs(o.double(), d.double(), eu[:, :-1], eu[:, 1:] - eu[:, :-1], cam, return_alphas=True, return_occupancy=True)
+    return sb, field, rs, out, e64, (o, d, cam, eu, o64)
+
+
+@pytest.mark.parametrize("name", ["neusfacto_c1", "neusfacto_c1_init"])
+def test_field_tc_bf16x3_matches_reference(name):
+    sb, field, rs, out, e64, (o, d, cam, eu, o64) = _run_case(name, "bf16x3")
+    G = load_golden(name)  # the unmodified reference's fp32 outputs on the same samples
+    H = sb.FieldHeadNames
+    # per-sample heads: error vs the fp64 oracle bounded by max(1e-4 of the head's scale, 4x the reference's own fp32 noise)
+    for key, gk in ((H.SDF, "sdf"), (H.RGB, "rgb"), (H.ALPHA, "alphas"), (H.DENSITY, "density"), (H.GRADIENT, "gradients"),
+                    (H.NORMAL, "normals"), (H.OCCUPANCY, "occupancy")):
+        assert_within_noise(out[key], G[gk], e64[gk], f"{name}/{gk}", factor=4.0, floor=1e-4 * float(e64[gk].abs().max()))
+    # rendered image quantities: BASELINE north_star bound (1e-4 relative)
+    w = rs.get_weights_from_alphas(out[H.ALPHA])
+    img = sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, torch.ones(3, device="cuda"))
+    ow, _ = samplers.weights_from_alphas(e64["alphas"][..., 0])
+    orgb = render.render_rgb(e64["rgb"], ow[..., None], torch.ones(3, dtype=torch.float64))
+    assert rel_err(img["rgb"], orgb, 1e-2) < 1e-4
+    gw, _ = samplers.weights_from_alphas(G["alphas"][..., 0])
+    gdep = render.render_depth(gw[..., None], eu[:, :-1, None].float(), eu[:, 1:, None].float(), "expected")
+    odep = render.render_depth(ow[..., None], eu[:, :-1, None], eu[:, 1:, None], "expected")
+    assert_within_noise(img["depth"], gdep, odep, f"{name}/depth", factor=4.0, floor=1e-4 * float(odep.abs().max()))
+    # sdf-only mode of the kernel (sampler path): un-contracted positions, same arithmetic
+    sdf_u = field.get_sdf(rs)
+    e_sdf = o64.get_sdf(o.double(), d.double(), eu[:, :-1])
+    assert_within_noise(sdf_u[..., 0], G["get_sdf"][..., 0], e_sdf, f"{name}/get_sdf", factor=4.0, floor=1e-4 * float(e_sdf.abs().max()))
+
+
+def test_field_tc_bf16_fast_mode_psnr():
+    sb, field, rs, out, e64, _ = _run_case("neusfacto_c1", "bf16")
+    H = sb.FieldHeadNames
+    w = rs.get_weights_from_alphas(out[H.ALPHA])
+    img = sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, torch.ones(3, device="cuda"))
+    ow, _ = samplers.weights_from_alphas(e64["alphas"][..., 0])
+    orgb = render.render_rgb(e64["rgb"], ow[..., None], torch.ones(3, dtype=torch.float64))
+    mse = float(((img["rgb"].cpu().double() - orgb) ** 2).mean())
+    psnr = -10.0 * torch.log10(torch.tensor(mse)).item()
+    assert psnr > 60.0, f"fast-mode PSNR vs reference {psnr:.1f} dB"
+
+
+def test_field_tc_ragged_tail_and_point_mode():
+    """N not a multiple of the 128-point tile; point-mode entry (forward_geonetwork / gradient)."""
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case("neusfacto_c1", precision="bf16x3")
+    G = load_golden("neusfacto_c1")
+    pts = G["points"].cuda()  # 200 points
+    geo = field.forward_geonetwork(pts)
+    o64 = oracle64(spec, oracle.p, kw)
+    assert_within_noise(geo, G["geo_points"], o64.forward_geonetwork(G["points"].double()), "forward_geonetwork", factor=4.0, floor=2e-5)
+    assert_within_noise(field.gradient(pts), G["grad_points"], o64.gradient(G["points"].double()), "gradient()", factor=4.0, floor=2e-5)
+    rb = make_bundle(o[:37], d[:37], cam[:37], nears[:37], fars[:37])
+    rs = sb.UniformSampler(num_samples=5).eval()(rb)  # 185 points
+    out = field(rs, return_alphas=True)
+    ob = samplers.spaced_sampler(nears[:37], fars[:37], 5, "uniform")
+    oo = oracle.get_outputs(o[:37], d[:37], ob.starts, ob.deltas, cam[:37], return_alphas=True)
+    assert rel_err(out[sb.FieldHeadNames.RGB], oo["rgb"], 1e-2) < 1e-3
+    assert rel_err(out[sb.FieldHeadNames.SDF], oo["sdf"], 1e-3) < 1e-3
