@@ -58,6 +58,22 @@ def oracle_of(field):
     return OracleField(spec, sd)
 
 
+def read_traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the field kernel from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", f"r01_ncu_field_tc_{precision}_summary.json")
+    if not os.path.exists(p):
+        return None
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        def mb(k):
+            v, u = float(d[k]["value"]), d[k]["unit"]
+            return v * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[u]
+        return mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def read_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,8 +321,8 @@ def main():
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16_tflops_sustained",
-                         "kernel": "sdfb200_field_forward (all kernels of the field call)", "ms_per_launch": fld_ms / args.steps,
+                         "frac": achieved_tflops / peaks["bf16_tflops_sustained"], "traffic": read_traffic(precision), "peak_source": peaks["source"] + " bf16_tflops_sustained",
+                         "kernel": "k_field_tc (sdfb200_field_forward)" if precision != "fp32" else "sdfb200_field_forward (k_sgemm + elementwise kernels)", "ms_per_launch": fld_ms / args.steps,
                          "algorithmic_flop_per_launch": flop_per_launch},
             "cpu_baseline": cpu, "clocks": clk,
         }  # fmt: skip

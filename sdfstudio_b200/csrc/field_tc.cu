@@ -52,6 +52,7 @@ struct TcArgs {
   int use_grid, pe_degree, use_pe, contraction, in_dim, pe_dim, grid_dim, cm_dim, app_dim, use_n_dot_v;
   int mode;  // 0: sdf only (G0, G1)   1: everything
   int timing;
+  int pol_table, pol_scratch;   // L2 policies: 0 normal, 1 evict_first, 2 evict_last
   int n_samples, has_bins, n_tiles;
   long long n_points;
   float rgb_padding, cos_anneal;
@@ -92,6 +93,10 @@ __device__ long long g_tc_timing[16 * 32];
   do {                                                                                    \
     if (a.timing && blockIdx.x == 0 && tid == 0 && tile_no < 16) g_tc_timing[tile_no * 32 + (k)] = clock64(); \
   } while (0)
+
+__device__ __forceinline__ uint64_t l2_policy(int kind) {
+  return kind == 1 ? l2_policy_evict_first() : (kind == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
+}
 
 // softplus_100 and its derivative through MUFU ex2 / lg2 / rcp.  t = 100 z.  Absolute error ~1e-7 on h (the quantity
 // that feeds the next layer), i.e. at the level of fp32 rounding of the reference's own log1p(exp(.)).
@@ -179,7 +184,7 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
   const long long p_raw = (long long)tile * 128 + row;
   const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
   const PointGeom g = point_geom(a, p);
-  const uint64_t pol_stream = l2_policy_evict_first();
+  const uint64_t pol_stream = l2_policy(a.pol_scratch);
   if (slice < 4) {
     const int l = q + 4 * slice;
     if (l < a.grid.n_levels && a.grid_dim > 0) {
@@ -187,7 +192,7 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
       float dj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       if (a.use_grid && l < a.grid.active_levels) {
         const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;
-        encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy_evict_last());
+        encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
       }
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
@@ -383,7 +388,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
     uint8_t* gf_s = reinterpret_cast<uint8_t*>(sig_s) + 131072;                                          // [P][32 units][128][16 B]
     uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x encoder side buffers
     uint32_t dpar = 0;
-    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_stream = l2_policy(a.pol_scratch);
 
     // prologue: encode the first tile completely
     for (int sl = 0; sl < 7; ++sl) encode_slice<P>(a, blockIdx.x, sl, row, q, inA0, enc_s);
@@ -856,6 +861,8 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   a.in_dim = p.in_dim; a.pe_dim = p.pe_dim; a.grid_dim = p.grid_dim; a.cm_dim = t.cm_dim; a.app_dim = f.appearance_dim; a.use_n_dot_v = f.use_n_dot_v;
   a.mode = sdf_only ? 0 : 1;
   a.timing = getenv("SDFB200_TC_TIMING") != nullptr;
+  a.pol_table = getenv("SDFB200_POL_TABLE") ? atoi(getenv("SDFB200_POL_TABLE")) : 2;
+  a.pol_scratch = getenv("SDFB200_POL_SCRATCH") ? atoi(getenv("SDFB200_POL_SCRATCH")) : 1;
   a.n_samples = in.n_samples; a.has_bins = in.bins != nullptr; a.n_points = N; a.n_tiles = (int)ceil_div(N, 128);
   a.rgb_padding = f.rgb_padding; a.cos_anneal = in.cos_anneal_ratio;
   a.origins = in.origins; a.directions = in.directions; a.bins = in.bins; a.appearance = in.appearance; a.variance = in.variance; a.beta = in.beta;
