@@ -243,8 +243,7 @@ def main():
         if time_field:
             e1.record()
             field_ms.append((e0, e1))
-        w = rs.get_weights_from_alphas(out[H.ALPHA])
-        return sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, white)
+        return sb.render_from_alphas(out[H.ALPHA], out[H.RGB], out[H.NORMAL], rs, white)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 

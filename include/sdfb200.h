@@ -234,6 +234,14 @@ typedef struct sdfb200_render_out {
 int sdfb200_render(const float* weights, const float* rgb, const float* normals, const float* euclid_bins,
                    const float* bg, int32_t bg_mode, int32_t clamp01, int32_t depth_median, int64_t n_rays,
                    int32_t n_samples, const sdfb200_render_out_t* out, void* stream);
+/* fused form of what SurfaceModel.get_outputs does after the field (models/neus.py:100-103 +
+ * models/base_surface_model.py:300-310): alphas [R,S] -> transmittance (rays.py:194-230) -> weights [R,S] (optional out) ->
+ * rgb / expected depth / normal / accumulation, one warp per ray.  bg_transmittance [R] (optional) = transmittance[:, -1].
+ * The prefix product is a warp scan in double (not the sequential order of torch.cumprod): results agree with
+ * sdfb200_weights_from_alphas + sdfb200_render to ~1e-7 relative, not bit-exactly. */
+int sdfb200_render_alphas(const float* alphas, const float* rgb, const float* normals, const float* euclid_bins,
+                          const float* bg, int32_t bg_mode, int32_t clamp01, int64_t n_rays, int32_t n_samples,
+                          float* weights, float* bg_transmittance, const sdfb200_render_out_t* out, void* stream);
 /* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
 int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
 

@@ -16,7 +16,7 @@ from .ray_samplers import (  # noqa: F401
     ErrorBoundedSampler, LinearDisparitySampler, LogSampler, NeuSSampler, PDFSampler, ProposalNetworkSampler, Sampler, SpacedSampler,
     SqrtSampler, UniformLinDispPiecewiseSampler, UniformSampler, UniSurfSampler,
 )
-from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, SemanticRenderer, render_all  # noqa: F401
+from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, SemanticRenderer, render_all, render_from_alphas  # noqa: F401
 from .sdf_field import LaplaceDensity, SDFField, SDFFieldConfig, SingleVarianceNetwork  # noqa: F401
 
 __version__ = "0.1.0"

@@ -94,6 +94,7 @@ _PROTOS = {
     "sdfb200_weights_from_alphas": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "sdfb200_weights_from_density": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp]),
     "sdfb200_render": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, C.POINTER(RenderOut), _vp]),
+    "sdfb200_render_alphas": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, C.POINTER(RenderOut), _vp]),
     "sdfb200_depth_clip": (C.c_int, [_vp, _vp, _i64, _vp]),
     "sdfb200_debug_tc_timing": (C.c_int, [_vp]),
     "sdfb200_debug_tc_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

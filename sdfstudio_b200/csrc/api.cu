@@ -104,7 +104,9 @@ extern "C" int sdfb200_field_forward(const sdfb200_field_t* f, const void* packe
   const size_t lost = wsp - (uintptr_t)workspace;
   SDFB_REQUIRE(workspace_bytes > lost, "workspace too small");
   const size_t ws_floats = (workspace_bytes - lost) / sizeof(float);
-  if (f->precision != SDFB200_PRECISION_FP32)
+  // the tensor-core kernel never materialises the geo feature (colour layer 0 is pre-multiplied with the last geo layer);
+  // the rare callers that want it (forward_geonetwork) take the exact-fp32 kernels, which read the same packed blob
+  if (f->precision != SDFB200_PRECISION_FP32 && out->geo_feature == nullptr)
     return field_tc_forward(*f, p, (const char*)packed, table, *in, *out, (float*)wsp, ws_floats, (cudaStream_t)stream);
   return field_forward_fp32(*f, p, (const char*)packed, table, *in, *out, (float*)wsp, ws_floats, (cudaStream_t)stream);
 }

@@ -5,7 +5,8 @@
 //   encode   16 epilogue warps: position, contraction, PE, hash gathers (+ jacobian) -> bf16 split planes in smem
 //   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), next layer's A operand written to TMEM
 //   sdf      fp32 dot of h2 with row 0 of W2 on CUDA cores (exact fp32: the SDF drives NeuS alpha / Laplace density)
-//   G2       geo feature (256)               spilled (bf16 planes) to a per-CTA L2-resident scratch
+//   (no G2)  the geo feature is linear in h2, so colour layer 0 is pre-multiplied at pack time: Wc = Wgf W2', and h2 itself
+//            (bf16 planes) takes the L2-resident round trip across the reverse sweep
 //   B1 B0    reverse sweep: g2 = W2[0,:]*sp'(z2), g1 = (W1^T g2)*sp'(z1), gin = W0^T g1;  sp'(z1) spilled at G0
 //   grad     d sdf/dx = gin_x + PE jacobian + grid jacobian / 4      (what autograd computes at sdf_field.py:647-654)
 //   C0 C1    relu MLP on [x, dir-enc, grad, geo feature, appearance]; last 256->3 layer as fp32 dots; sigmoid + padding
@@ -32,13 +33,13 @@ constexpr int kMaxGridDim = 32;
 constexpr int kMaxPe = 64;         // PE columns (2 * 3 * degree)
 constexpr int kInK = 96;          // padded K of the two small-K operands (geo input, colour misc input)
 constexpr float kHalfPiF = 1.5707963267948966f;
-// per-CTA scratch: softplus'(z1) fp32 [128 KB] | geo-feature planes [P x 64 KB] | 2 x encoder side buffer
+// per-CTA scratch: softplus'(z1) unorm16 [64 KB] | h2 planes [P x 64 KB] | 2 x input jacobian
 // encoder side buffer: input jacobian (PE derivative [64][128] f32 | grid [96][128] f32) | static colour operand [P][11][128][16 B]
 constexpr size_t kJRBytes = (size_t)(kMaxPe + kMaxGridDim * 3) * 128 * 4;   // input jacobian: PE [64][128] f32 | grid [32*3][128] f32
-__host__ __device__ constexpr size_t kEncBufBytes(int planes) { return kJRBytes + (size_t)planes * 11 * 2048; }
-__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 131072 + (size_t)planes * 65536 + 2 * kEncBufBytes(planes); }
+__host__ __device__ constexpr size_t kEncBufBytes(int planes) { return kJRBytes; }
+__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 65536 + (size_t)planes * 65536 + 2 * kEncBufBytes(planes); }
 
-enum { L_G0 = 0, L_G1, L_G2, L_B1, L_B0, L_C0GF, L_C0MISC, L_C1, L_COUNT };
+enum { L_G0 = 0, L_G1, L_B1, L_B0, L_C0H, L_C0MISC, L_C1, L_COUNT };
 
 struct TcLayer {
   unsigned long long w_off;  // byte offset of the packed planes inside the blob
@@ -60,7 +61,7 @@ struct TcArgs {
   const void* table;
   const char* blob;
   // fp32 section offsets (bytes)
-  unsigned long long b_g0, b_g1, b_g2, w_g2, b_c0, b_c1, w_c2, b_c2;
+  unsigned long long b_g0, b_g1, b_g2, w_g2, b_c0, b_c1, w_c2, b_c2;   // b_c0 = fused bias (bc0 + Wgf b2')
   char* scratch;
   unsigned long long scratch_per_cta;
   sdfb200_field_out_t out;
@@ -98,32 +99,44 @@ __device__ __forceinline__ uint64_t l2_policy(int kind) {
   return kind == 1 ? l2_policy_evict_first() : (kind == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
 }
 
+// colour layer 0 pre-multiplied with the (activation-free) last geo layer: Wc[o][k] = sum_j Wc0[o][33+j] W2[1+j][k],
+// bias[o] = bc0[o] + sum_j Wc0[o][33+j] b2[1+j]        (sdf_field.py:406-410 feeds :576-592)
+__global__ void k_fuse_c0(const float* __restrict__ Wc0, int ldc0, const float* __restrict__ bc0, const float* __restrict__ W2, int ld2,
+                          const float* __restrict__ b2, float* __restrict__ Wc, float* __restrict__ bc) {
+  __shared__ float wrow[256];
+  const int o = blockIdx.x, k = threadIdx.x;
+  wrow[k] = Wc0[(size_t)o * ldc0 + 33 + k];
+  __syncthreads();
+  float acc = 0.f;
+  for (int j = 0; j < 256; ++j) acc = fmaf(wrow[j], W2[(size_t)(1 + j) * ld2 + k], acc);
+  Wc[o * 256 + k] = acc;
+  if (k == 0) {
+    float b = bc0[o];
+    for (int j = 0; j < 256; ++j) b = fmaf(wrow[j], b2[1 + j], b);
+    bc[o] = b;
+  }
+}
+
 // softplus_100 and its derivative through MUFU ex2 / lg2 / rcp.  t = 100 z.  Absolute error ~1e-7 on h (the quantity
 // that feeds the next layer), i.e. at the level of fp32 rounding of the reference's own log1p(exp(.)).
 __device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void softplus100_fast(float z, float& h, float& dsig) {
-  const float t = z * 100.0f;
-  const float e = fast_ex2(fminf(t, 30.0f) * 1.4426950408889634f);   // exp(t), clamped far above the threshold
+  // exp(100 z) = 2^(z * 100 log2 e); log1p(e)/100 = lg2(1+e) * ln2/100.  For small e, 1+e rounds e to ~6e-8 absolute, i.e. an
+  // absolute error of ~4e-10 on h: irrelevant next to the bf16x3 operand rounding (2^-17 relative).
+  const float e = fast_ex2(fminf(z, 0.3f) * 144.26950408889634f);
   const float u = 1.0f + e;
-  const bool lin = t > 20.0f;                                           // PyTorch's softplus threshold
-  // log1p(e): for small e, lg2(1+e) loses the low bits of e; the series e - e^2/2 is exact enough below 2^-10
-  const float l = e < 9.765625e-4f ? e * (1.0f - 0.5f * e) : fast_lg2(u) * 0.6931471805599453f;
-  h = lin ? z : l * 0.01f;
+  const bool lin = z > 0.2f;                                            // PyTorch's softplus threshold: beta*x > 20
+  h = lin ? z : fast_lg2(u) * 0.006931471805599453f;
   dsig = lin ? 1.0f : e * fast_rcp(u);
 }
 __device__ __forceinline__ float softplus100_fast_h(float z) {
-  const float t = z * 100.0f;
-  const float e = fast_ex2(fminf(t, 30.0f) * 1.4426950408889634f);
-  const float l = e < 9.765625e-4f ? e * (1.0f - 0.5f * e) : fast_lg2(1.0f + e) * 0.6931471805599453f;
-  return t > 20.0f ? z : l * 0.01f;
+  const float e = fast_ex2(fminf(z, 0.3f) * 144.26950408889634f);
+  return z > 0.2f ? z : fast_lg2(1.0f + e) * 0.006931471805599453f;
 }
-// softplus'(z) recovered from h = softplus(z):  1 - exp(-100 h)   (for tiny h: 100 h (1 - 50 h))
-__device__ __forceinline__ float dsoftplus_from_h_fast(float h) {
-  const float x = 100.0f * h;
-  return x < 1.953125e-3f ? x * (1.0f - 0.5f * x) : 1.0f - fast_ex2(-x * 1.4426950408889634f);
-}
+// softplus'(z) recovered from h = softplus(z):  1 - exp(-100 h)
+__device__ __forceinline__ float dsoftplus_from_h_fast(float h) { return 1.0f - fast_ex2(h * -144.26950408889634f); }
 
 __device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -180,11 +193,10 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
   if (tile >= a.n_tiles) return;
   float* Jpe = reinterpret_cast<float*>(enc);                       // [pe column][row]     d PE_i / d x_axis(i)
   float* Jg = Jpe + kMaxPe * 128;                                    // [grid col * 3 + d][row]
-  uint8_t* cms = enc + kJRBytes;                                    // [P][11][128][16 B]
   const long long p_raw = (long long)tile * 128 + row;
   const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
   const PointGeom g = point_geom(a, p);
-  const uint64_t pol_stream = l2_policy(a.pol_scratch);
+  const uint64_t pol_stream = l2_policy_evict_normal();   // jacobian / colour columns live for a whole tile: keep them in L2
   if (slice < 4) {
     const int l = q + 4 * slice;
     if (l < a.grid.n_levels && a.grid_dim > 0) {
@@ -222,7 +234,8 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
     }
   } else if (slice == 5) {
     if (a.mode != 0) {
-      // static colour columns (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(27) | appearance | 0
+      // static colour columns (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(27) | appearance | 0, for the CURRENT
+      // tile: `inA` is that tile's own operand buffer, whose geo input G0 has already consumed
       const float pc[3] = {g.px, g.py, g.pz};
       const float dd[3] = {g.dx, g.dy, g.dz};
       for (int ch = q; ch < 11; ch += 4) {
@@ -243,8 +256,8 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
           }
           split2(v2[0], v2[1], hi[e2], lo[e2]);
         }
-        st_stream(cms + ((size_t)ch * 128 + row) * 16, make_uint4(hi[0], hi[1], hi[2], hi[3]), pol_stream);
-        if (P > 1) st_stream(cms + (size_t)11 * 2048 + ((size_t)ch * 128 + row) * 16, make_uint4(lo[0], lo[1], lo[2], lo[3]), pol_stream);
+        *reinterpret_cast<uint4*>(inA + (size_t)(1 + ch) * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + (size_t)(1 + ch) * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
   } else {
@@ -254,7 +267,6 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
       for (int c = a.in_dim; c < kInK; ++c) store_in<P>(inA, row, c, 0.f);
     }
     fence_async_smem();                                        // smem operand -> async proxy (UMMA reads it)
-    asm volatile("fence.proxy.async.global;" ::: "memory");    // scratch -> async proxy (bulk copy of the colour columns)
   }
 }
 
@@ -268,21 +280,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
   float* fbuf = reinterpret_cast<float*>(ring + kStages * kStageBytes);
   float* red = fbuf;                  // [3][4][128] partial sums
   float* prm = fbuf + 12 * 128;       // [9][256] biases / fp32 weight rows used by the epilogues
-  __shared__ uint64_t full[kStages], empty[kStages], dfull, cm_full;
+  __shared__ uint64_t full[kStages], empty[kStages], dfull;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&dfull, 1);
-    mbar_init(&cm_full, 1);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   {
     const char* blob = a.blob;
     const float* src[9] = {reinterpret_cast<const float*>(blob + a.b_g0), reinterpret_cast<const float*>(blob + a.b_g1),
-                           reinterpret_cast<const float*>(blob + a.b_g2) + 1, reinterpret_cast<const float*>(blob + a.w_g2),
+                           reinterpret_cast<const float*>(blob + a.b_g1), reinterpret_cast<const float*>(blob + a.w_g2),
                            reinterpret_cast<const float*>(blob + a.b_c0), reinterpret_cast<const float*>(blob + a.b_c1),
                            reinterpret_cast<const float*>(blob + a.w_c2), reinterpret_cast<const float*>(blob + a.w_c2) + 256,
                            reinterpret_cast<const float*>(blob + a.w_c2) + 512};
@@ -328,7 +339,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
           tc_fence_after();
         }
         if (lane == 0) {
-          if (L == L_C0MISC) { mbar_wait(&cm_full, tile_no & 1); tc_fence_after(); }
           const TcLayer ly = a.layer[L];
           const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
           const uint32_t idesc = make_idesc_bf16(128, ly.Np);
@@ -364,7 +374,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
             }
             mma_commit(&empty[s]);
           }
-          if (L != L_C0GF) mma_commit(&dfull);            // C0GF is completed by C0MISC
+          if (L != L_C0H) mma_commit(&dfull);             // C0H is completed by C0MISC
         }
         __syncwarp();
       }
@@ -377,7 +387,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
     const char* blob = a.blob;
     const float* p_bg0 = prm;             // smem copies (broadcast LDS.128 instead of one LDG per element)
     const float* p_bg1 = prm + 256;
-    const float* p_bg2 = prm + 512;       // geo-feature bias (b_g2[1..])
     const float* p_wg2 = prm + 768;       // row 0 of the last geo layer
     const float* p_bc0 = prm + 1024;
     const float* p_bc1 = prm + 1280;
@@ -385,13 +394,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
     const float sdf_bias = __ldg(reinterpret_cast<const float*>(blob + a.b_g2));
     const float* b_c2 = reinterpret_cast<const float*>(blob + a.b_c2);
     float* sig_s = reinterpret_cast<float*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);        // [64 units][128 rows][4]
-    uint8_t* gf_s = reinterpret_cast<uint8_t*>(sig_s) + 131072;                                          // [P][32 units][128][16 B]
+    uint8_t* gf_s = reinterpret_cast<uint8_t*>(sig_s) + 65536;                                          // [P][32 units][128][16 B]
     uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x encoder side buffers
     uint32_t dpar = 0;
     const uint64_t pol_stream = l2_policy(a.pol_scratch);
 
     // prologue: encode the first tile completely
-    for (int sl = 0; sl < 7; ++sl) encode_slice<P>(a, blockIdx.x, sl, row, q, inA0, enc_s);
+    for (int sl = 0; sl < 7; ++sl)
+      if (sl != 5) encode_slice<P>(a, blockIdx.x, sl, row, q, inA0, enc_s);
 
     int tile_no = -1;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -421,14 +431,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       // ---------------- E0: h1 = softplus(z1) -> A planes ; softplus'(z1) -> scratch ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(2);
-      if (a.mode != 0 && tid == 0) {
-        // G0 has consumed the geo input: chunks 1..11 of this buffer take the static colour columns prepared one tile ago
-        // (bulk copy global scratch -> smem, completes on cm_full; C0MISC waits for it)
-        const uint8_t* cms = enc_cur + kJRBytes;
-        mbar_arrive_expect_tx(&cm_full, (uint32_t)P * 11 * 2048);
-#pragma unroll
-        for (int pl = 0; pl < P; ++pl) bulk_g2s(inA + pl * (kInK / 8) * 2048 + 2048, cms + (size_t)pl * 11 * 2048, 11 * 2048, &cm_full);
-      }
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
@@ -452,8 +454,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
         if (a.mode != 0) {
 #pragma unroll
-          for (int u4 = 0; u4 < 4; ++u4)
-            st_stream(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4, make_float4(sg[4 * u4], sg[4 * u4 + 1], sg[4 * u4 + 2], sg[4 * u4 + 3]), pol_stream);
+          for (int u8 = 0; u8 < 2; ++u8) {
+            // 8 values -> 8 x unorm16 (one 16-byte unit per thread): absolute error 2^-17
+            uint32_t pk[4];
+#pragma unroll
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const uint32_t lo16 = __float2uint_rn(sg[u8 * 8 + 2 * e2] * 65535.0f), hi16 = __float2uint_rn(sg[u8 * 8 + 2 * e2 + 1] * 65535.0f);
+              pk[e2] = lo16 | (hi16 << 16);
+            }
+            st_stream(reinterpret_cast<uint8_t*>(sig_s) + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+          }
         }
       }
       tc_wait_st();
@@ -461,9 +471,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       named_arrive(1, kEpiThreads + 32);
       TC_STAMP(3);
       if (a.mode == 0) { encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 6, row, q, inA_next, enc_next); }
-      else encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next);
+      else {
+        encode_slice<P>(a, tile, 5, row, q, inA, enc_cur);          // this tile's static colour columns, in place (G0 is done)
+        encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next);
+      }
 
-      // ---------------- E1: h2 -> A planes ; sdf = W2[0,:] . h2 + b (fp32) ----------------
+      // ---------------- E1: h2 -> scratch planes (colour layer 0 input) ; sdf = W2[0,:] . h2 + b (fp32) ;
+      //                      g2 = W2[0,:] * softplus'(z2) -> A planes (seed of the reverse sweep)
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(4);
       float sdf_part = 0.f;
@@ -473,20 +487,35 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
-        uint32_t hi[8], lo[8];
+        uint32_t hi[8], lo[8], ghi[8], glo[8];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
           const float4 b4 = *reinterpret_cast<const float4*>(p_bg1 + col0 + j);
           const float4 w4 = *reinterpret_cast<const float4*>(p_wg2 + col0 + j);
-          const float h0 = softplus100_fast_h(__uint_as_float(v[j]) + b4.x), h1 = softplus100_fast_h(__uint_as_float(v[j + 1]) + b4.y);
-          const float h2 = softplus100_fast_h(__uint_as_float(v[j + 2]) + b4.z), h3 = softplus100_fast_h(__uint_as_float(v[j + 3]) + b4.w);
+          float h0, h1, h2, h3, s0, s1, s2, s3;
+          softplus100_fast(__uint_as_float(v[j]) + b4.x, h0, s0);
+          softplus100_fast(__uint_as_float(v[j + 1]) + b4.y, h1, s1);
+          softplus100_fast(__uint_as_float(v[j + 2]) + b4.z, h2, s2);
+          softplus100_fast(__uint_as_float(v[j + 3]) + b4.w, h3, s3);
           sdf_part = fmaf(w4.x, h0, sdf_part); sdf_part = fmaf(w4.y, h1, sdf_part);
           sdf_part = fmaf(w4.z, h2, sdf_part); sdf_part = fmaf(w4.w, h3, sdf_part);
           split2(h0, h1, hi[j >> 1], lo[j >> 1]);
           split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
+          if (a.mode != 0) {
+            split2(w4.x * s0, w4.y * s1, ghi[j >> 1], glo[j >> 1]);
+            split2(w4.z * s2, w4.w * s3, ghi[(j >> 1) + 1], glo[(j >> 1) + 1]);
+          }
         }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
+        if (a.mode != 0) {
+#pragma unroll
+          for (int u8 = 0; u8 < 2; ++u8) {
+            const size_t unit = ((size_t)((col0 >> 3) + u8) * 128 + row) * 16;
+            st_stream(gf_s + unit, make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]), pol_stream);
+            if (P > 1) st_stream(gf_s + 65536 + unit, make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]), pol_stream);
+          }
+          tmem_st8(a_tmem + lane_addr + (col0 >> 1), ghi);
+          if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), glo);
+        }
       }
       tc_wait_st();
       red[q * 128 + row] = sdf_part;
@@ -501,53 +530,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         continue;
       }
       encode_slice<P>(a, next_tile, 2, row, q, inA_next, enc_next);
-
-      // ---------------- E2: geo feature -> scratch planes ; g2 = W2[0,:] * softplus'(z2) -> A planes ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(6);
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = q * 64 + cc * 16;
-        uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float2 b2 = *reinterpret_cast<const float2*>(p_bg2 + col0 + j);
-          const float g0 = __uint_as_float(v[j]) + b2.x;
-          const float g1 = __uint_as_float(v[j + 1]) + b2.y;
-          if (a.out.geo_feature && valid) { a.out.geo_feature[p * 256 + col0 + j] = g0; a.out.geo_feature[p * 256 + col0 + j + 1] = g1; }
-          split2(g0, g1, hi[j >> 1], lo[j >> 1]);
-        }
-#pragma unroll
-        for (int u8 = 0; u8 < 2; ++u8) {
-          const size_t unit = ((size_t)((col0 >> 3) + u8) * 128 + row) * 16;
-          st_stream(gf_s + unit, make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]), pol_stream);
-          if (P > 1) st_stream(gf_s + 65536 + unit, make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]), pol_stream);
-        }
-        // h2 (A planes) -> g2 in place.  softplus'(z) = 1 - exp(-100 h)
-        uint32_t h_hi[8], h_lo[8];
-        tmem_ld8(a_tmem + lane_addr + (col0 >> 1), h_hi);
-        if (P > 1) tmem_ld8(a_tmem + 128 + lane_addr + (col0 >> 1), h_lo);
-        tc_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float ha = bf16lo_to_f32(h_hi[j]), hb = bf16hi_to_f32(h_hi[j]);
-          if (P > 1) { ha += bf16lo_to_f32(h_lo[j]); hb += bf16hi_to_f32(h_lo[j]); }
-          const float2 w2 = *reinterpret_cast<const float2*>(p_wg2 + col0 + 2 * j);
-          const float ga = w2.x * dsoftplus_from_h_fast(ha);
-          const float gb = w2.y * dsoftplus_from_h_fast(hb);
-          split2(ga, gb, hi[j], lo[j]);
-        }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
-      }
-      tc_wait_st();
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
       TC_STAMP(7);
-      encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next);
 
       // ---------------- EB1: g1 = (W1^T g2) * softplus'(z1) -> A planes ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
@@ -555,17 +539,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
 #pragma unroll
       for (int cc = 0; cc < 4; ++cc) {
         const int col0 = q * 64 + cc * 16;
-        float4 s4[4];
+        uint4 sp[2];
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) s4[u4] = ld_stream_f4(sig_s + ((size_t)((col0 >> 2) + u4) * 128 + row) * 4, pol_stream);
+        for (int u8 = 0; u8 < 2; ++u8) sp[u8] = ld_stream_u4(reinterpret_cast<const uint8_t*>(sig_s) + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, pol_stream);
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
         uint32_t hi[8], lo[8];
+        const uint32_t spw[8] = {sp[0].x, sp[0].y, sp[0].z, sp[0].w, sp[1].x, sp[1].y, sp[1].z, sp[1].w};
 #pragma unroll
-        for (int u4 = 0; u4 < 4; ++u4) {
-          split2(__uint_as_float(v[4 * u4]) * s4[u4].x, __uint_as_float(v[4 * u4 + 1]) * s4[u4].y, hi[2 * u4], lo[2 * u4]);
-          split2(__uint_as_float(v[4 * u4 + 2]) * s4[u4].z, __uint_as_float(v[4 * u4 + 3]) * s4[u4].w, hi[2 * u4 + 1], lo[2 * u4 + 1]);
+        for (int j = 0; j < 8; ++j) {
+          const float s0 = (float)(spw[j] & 0xFFFFu) * (1.0f / 65535.0f), s1 = (float)(spw[j] >> 16) * (1.0f / 65535.0f);
+          split2(__uint_as_float(v[2 * j]) * s0, __uint_as_float(v[2 * j + 1]) * s1, hi[j], lo[j]);
         }
         tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
@@ -574,7 +559,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
       TC_STAMP(9);
-      encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next);
+      encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next);
 
       // ---------------- EB0: gin (96 cols) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ; geo feature reload
       // the jacobian units and the geo-feature planes do not depend on this phase's MMA: fetch them before waiting
@@ -583,53 +568,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       const float* Jpe = reinterpret_cast<const float*>(enc_cur);
       const float* Jg = Jpe + kMaxPe * 128;
       const int deg = a.pe_degree, half = 3 * deg;
-      auto load_jac = [&](int c0, float (&jf)[24]) {
+      const uint64_t pol_keep = l2_policy_evict_normal();
+      float gx = 0.f, gy = 0.f, gz = 0.f;
+      uint32_t gin_v[8];
+#pragma unroll
+      for (int c8 = 0; c8 < 3; ++c8) {
+        const int c0 = q * 24 + c8 * 8;
+        // predicated (branch-free) fetch of this batch's jacobian entries: every load is issued before the first use
+        float jx[8], jy[8], jz[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = c0 + j;
-          float jx = 0.f, jy = 0.f, jz = 0.f;
-          if (c < 3) {
-            jx = c == 0 ? 1.f : 0.f; jy = c == 1 ? 1.f : 0.f; jz = c == 2 ? 1.f : 0.f;
-          } else if (c < 3 + a.pe_dim) {
-            int i = c - 3;
-            const float dv = ld_stream_f1(Jpe + i * 128 + row, pol_stream);
-            if (i >= half) i -= half;
-            jx = i < deg ? dv : 0.f; jy = (i >= deg && i < 2 * deg) ? dv : 0.f; jz = i >= 2 * deg ? dv : 0.f;
-          } else if (c < a.in_dim) {
-            const int cg = c - 3 - a.pe_dim;
-            jx = ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_stream);
-            jy = ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_stream);
-            jz = ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_stream);
-          }
-          jf[3 * j] = jx; jf[3 * j + 1] = jy; jf[3 * j + 2] = jz;
+          const bool is_pe = c >= 3 && c < 3 + a.pe_dim;
+          const bool is_grid = c >= 3 + a.pe_dim && c < a.in_dim;
+          const int i = c - 3, cg = c - 3 - a.pe_dim;
+          const int ia = i >= half ? i - half : i;                       // axis block of a PE column
+          const float dv = is_pe ? ld_stream_f1(Jpe + i * 128 + row, pol_keep) : 0.f;
+          const float g0 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_keep) : 0.f;
+          const float g1 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_keep) : 0.f;
+          const float g2 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_keep) : 0.f;
+          jx[j] = c == 0 ? 1.f : (is_pe && ia < deg ? dv : g0);
+          jy[j] = c == 1 ? 1.f : (is_pe && ia >= deg && ia < 2 * deg ? dv : g1);
+          jz[j] = c == 2 ? 1.f : (is_pe && ia >= 2 * deg ? dv : g2);
         }
-      };
-      float jf0[24];
-      load_jac(q * 24, jf0);                              // independent of this phase's MMA: fetch before waiting
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(10);
-      {
-        float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll
-        for (int c8 = 0; c8 < 3; ++c8) {
-          uint32_t v[8];
-          tmem_ld8(d_tmem + lane_addr + q * 24 + c8 * 8, v);
-          float jf1[24];
-          if (c8 < 2) load_jac(q * 24 + (c8 + 1) * 8, jf1);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float g = __uint_as_float(v[j]);
-            gx = fmaf(g, jf0[3 * j], gx); gy = fmaf(g, jf0[3 * j + 1], gy); gz = fmaf(g, jf0[3 * j + 2], gz);
-          }
-          if (c8 < 2) {
-#pragma unroll
-            for (int j = 0; j < 24; ++j) jf0[j] = jf1[j];
-          }
+        if (c8 == 0) {
+          mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+          TC_STAMP(10);
         }
-        red[(0 * 4 + q) * 128 + row] = gx; red[(1 * 4 + q) * 128 + row] = gy; red[(2 * 4 + q) * 128 + row] = gz;
+        tmem_ld8(d_tmem + lane_addr + c0, gin_v);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float g = __uint_as_float(gin_v[j]);
+          gx = fmaf(g, jx[j], gx); gy = fmaf(g, jy[j], gy); gz = fmaf(g, jz[j], gz);
+        }
       }
-      // geo feature planes back into the A operand (all L2 loads in flight before the first TMEM store)
+      red[(0 * 4 + q) * 128 + row] = gx; red[(1 * 4 + q) * 128 + row] = gy; red[(2 * 4 + q) * 128 + row] = gz;
+      // h2 planes back into the A operand for colour layer 0 (all L2 loads in flight before the first TMEM store)
       {
         uint4 gh[8], gl[8];
 #pragma unroll
@@ -668,7 +643,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       tc_fence_before();
       named_arrive(1, kEpiThreads + 32);
       TC_STAMP(11);
-      encode_slice<P>(a, next_tile, 5, row, q, inA_next, enc_next);
+      encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next);
 
       // ---------------- EC0: relu -> A planes ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
@@ -760,15 +735,15 @@ static size_t tc_layer_bytes(int planes, int Np, int nkb) { return (size_t)nkb *
 struct TcPlan {
   int planes;
   TcLayer layer[L_COUNT];
-  size_t total;
+  size_t total, wc_off, bc_off;
   int cm_dim;
 };
 
 static void make_tc_plan(const sdfb200_field_t& f, const FieldPlan& p, TcPlan& t) {
   t.planes = f.precision == SDFB200_PRECISION_BF16X3 ? 2 : 1;
   t.cm_dim = 3 + 27 + 3 + f.appearance_dim + (f.use_n_dot_v ? 1 : 0);
-  const int np[L_COUNT] = {256, 256, 256, 256, kInK, 256, 256, 256};
-  const int nkb[L_COUNT] = {kInK / kKB, 8, 8, 8, 8, 8, kInK / kKB, 8};
+  const int np[L_COUNT] = {256, 256, 256, kInK, 256, 256, 256};
+  const int nkb[L_COUNT] = {kInK / kKB, 8, 8, 8, 8, kInK / kKB, 8};
   size_t off = p.tc_off;
   for (int l = 0; l < L_COUNT; ++l) {
     t.layer[l].w_off = off;
@@ -776,6 +751,10 @@ static void make_tc_plan(const sdfb200_field_t& f, const FieldPlan& p, TcPlan& t
     t.layer[l].nkb = nkb[l];
     off = align_up(off + tc_layer_bytes(t.planes, np[l], nkb[l]), 256);
   }
+  t.wc_off = off;                       // fp32 [256][256]: Wgf * W2[1:,:]   (colour layer 0 applied to h2 directly)
+  off = align_up(off + 256 * 256 * 4, 256);
+  t.bc_off = off;                       // fp32 [256]: bc0 + Wgf * b2[1:]
+  off = align_up(off + 256 * 4, 256);
   t.total = off - p.tc_off;
 }
 
@@ -820,11 +799,13 @@ int field_tc_pack(const sdfb200_field_t& f, const FieldPlan& p, char* blob, cuda
   int r;
   if ((r = pack(L_G0, (const float*)(blob + g0.w_off), g0.Kp, 256, g0.K, nullptr))) return r;
   if ((r = pack(L_G1, (const float*)(blob + g1.w_off), g1.Kp, 256, 256, nullptr))) return r;
-  if ((r = pack(L_G2, (const float*)(blob + g2.w_off) + g2.Kp, g2.Kp, 256, 256, nullptr))) return r;      // rows 1..256 (geo feature)
   if ((r = pack(L_B1, (const float*)(blob + g1.wt_off), g1.Np, 256, 256, nullptr))) return r;              // W1^T: [in][out]
   if ((r = pack(L_B0, (const float*)(blob + g0.wt_off), g0.Np, g0.K, 256, nullptr))) return r;             // W0^T: rows = input index
   // colour layer 0 (sdf_field.py:572-584): reference input = [x(3) dir(27) grad(3) | geo feature(256) | appearance | n.v]
-  if ((r = pack(L_C0GF, (const float*)(blob + c0.w_off) + 33, c0.Kp, 256, 256, nullptr))) return r;
+  k_fuse_c0<<<256, 256, 0, st>>>((const float*)(blob + c0.w_off), c0.Kp, (const float*)(blob + c0.b_off), (const float*)(blob + g2.w_off), g2.Kp,
+                                 (const float*)(blob + g2.b_off), (float*)(blob + t.wc_off), (float*)(blob + t.bc_off));
+  SDFB_LAUNCHED("k_fuse_c0");
+  if ((r = pack(L_C0H, (const float*)(blob + t.wc_off), 256, 256, 256, nullptr))) return r;
   // misc operand, kernel order: chunk 0 = [grad(3), n.v, 0 x4] (written per tile by the epilogue), then the static part
   // [x(3), dir-enc(27), appearance] prepared by the encoder warps
   ColMap cm;
@@ -846,7 +827,8 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   make_tc_plan(f, p, t);
   const size_t per_cta = kScratchPerCta(t.planes);
   if (ws_floats * sizeof(float) < (size_t)kNumSMs * per_cta) return fail(SDFB200_EWORKSPACE, "workspace too small for the tensor-core path%s", "", 0);
-  const bool sdf_only = out.sdf && !out.geo_feature && !out.gradients && !out.normals && !out.rgb && !out.density && !out.alpha && !out.occupancy;
+  SDFB_REQUIRE(out.geo_feature == nullptr, "geo_feature is not produced by the tensor-core path (use precision fp32)");
+  const bool sdf_only = out.sdf && !out.gradients && !out.normals && !out.rgb && !out.density && !out.alpha && !out.occupancy;
   if (!sdf_only) {
     if (out.rgb || out.alpha) SDFB_REQUIRE(in.directions != nullptr, "directions required for rgb / alpha");
     if (out.alpha) SDFB_REQUIRE(in.bins != nullptr && in.variance != nullptr, "alpha needs bins and the variance parameter");
@@ -868,7 +850,7 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   a.origins = in.origins; a.directions = in.directions; a.bins = in.bins; a.appearance = in.appearance; a.variance = in.variance; a.beta = in.beta;
   a.beta_min = in.beta_min; a.table = table; a.blob = blob;
   a.b_g0 = p.geo[0].b_off; a.b_g1 = p.geo[1].b_off; a.b_g2 = p.geo[2].b_off; a.w_g2 = p.geo[2].w_off;
-  a.b_c0 = p.col[0].b_off; a.b_c1 = p.col[1].b_off; a.w_c2 = p.col[2].w_off; a.b_c2 = p.col[2].b_off;
+  a.b_c0 = t.bc_off; a.b_c1 = p.col[1].b_off; a.w_c2 = p.col[2].w_off; a.b_c2 = p.col[2].b_off;
   a.scratch = reinterpret_cast<char*>(ws); a.scratch_per_cta = per_cta; a.out = out;
   const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
   const size_t smem = 2 * (size_t)t.planes * (kInK / 8) * 2048 + (size_t)kStages * t.planes * 256 * kKB * 2 + 12 * 128 * 4 + 9 * 256 * 4 + 1024;

@@ -124,6 +124,76 @@ __global__ void __launch_bounds__(128) k_render(const RenderArgs a) {
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// fused alpha -> transmittance -> weights -> composite, ONE WARP PER RAY (coalesced: lane = sample % 32; the running
+// transmittance is a warp-level prefix product in double, carried across 32-sample rows).  What SurfaceModel.get_outputs does
+// with get_weights_and_transmittance_from_alphas + four renderers (models/neus.py:100-103, base_surface_model.py:300-310).
+// -----------------------------------------------------------------------------------------------------------------
+struct RenderAlphaArgs {
+  const float* alphas; const float* rgb; const float* normals; const float* eu; const float* bg;
+  int bg_mode, clamp01; int64_t R; int S;
+  float *o_weights, *o_rgb, *o_depth, *o_normal, *o_acc, *o_bgT, *o_minmax;
+};
+__global__ void __launch_bounds__(256) k_render_alphas(const RenderAlphaArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= a.R) return;  // whole warp
+  const int S = a.S;
+  double carry = 1.0;
+  float cr = 0.f, cg = 0.f, cb = 0.f, acc = 0.f, dsum = 0.f, nx = 0.f, ny = 0.f, nz = 0.f, smin = INFINITY, smax = -INFINITY;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int s = s0 + lane;
+    const bool on = s < S;
+    const float al = on ? a.alphas[r * S + s] : 0.f;
+    double f = on ? (double)__fadd_rn(__fsub_rn(1.0f, al), 1e-7f) : 1.0;   // rays.py:204-206
+    double incl = f;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double o = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl *= o;
+    }
+    double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.0;
+    const float T = (float)(carry * excl);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    const float w = __fmul_rn(al, T);
+    if (on) {
+      if (a.o_weights) a.o_weights[r * S + s] = w;
+      acc += w;
+      if (a.rgb) { const float* c = a.rgb + (r * S + s) * 3; cr = fmaf(w, c[0], cr); cg = fmaf(w, c[1], cg); cb = fmaf(w, c[2], cb); }
+      if (a.normals) { const float* n = a.normals + (r * S + s) * 3; nx = fmaf(w, n[0], nx); ny = fmaf(w, n[1], ny); nz = fmaf(w, n[2], nz); }
+      if (a.eu) {
+        const float step = __fdiv_rn(__fadd_rn(a.eu[r * (S + 1) + s], a.eu[r * (S + 1) + s + 1]), 2.0f);
+        dsum = fmaf(w, step, dsum);
+        smin = fminf(smin, step); smax = fmaxf(smax, step);
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    cr += __shfl_xor_sync(0xffffffffu, cr, d); cg += __shfl_xor_sync(0xffffffffu, cg, d); cb += __shfl_xor_sync(0xffffffffu, cb, d);
+    nx += __shfl_xor_sync(0xffffffffu, nx, d); ny += __shfl_xor_sync(0xffffffffu, ny, d); nz += __shfl_xor_sync(0xffffffffu, nz, d);
+    acc += __shfl_xor_sync(0xffffffffu, acc, d); dsum += __shfl_xor_sync(0xffffffffu, dsum, d);
+    smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, d)); smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+  }
+  if (lane == 0) {
+    if (a.o_rgb && a.rgb) {
+      float bgc[3] = {0.f, 0.f, 0.f};
+      if (a.bg_mode == SDFB200_BG_COLOR) { bgc[0] = a.bg[0]; bgc[1] = a.bg[1]; bgc[2] = a.bg[2]; }
+      else if (a.bg_mode == SDFB200_BG_PER_RAY) { bgc[0] = a.bg[r * 3]; bgc[1] = a.bg[r * 3 + 1]; bgc[2] = a.bg[r * 3 + 2]; }
+      else { const float* c = a.rgb + (r * S + S - 1) * 3; bgc[0] = c[0]; bgc[1] = c[1]; bgc[2] = c[2]; }
+      const float rem = 1.0f - acc;
+      const float o[3] = {cr + bgc[0] * rem, cg + bgc[1] * rem, cb + bgc[2] * rem};
+      for (int c = 0; c < 3; ++c) a.o_rgb[r * 3 + c] = a.clamp01 ? fminf(fmaxf(o[c], 0.f), 1.f) : o[c];
+    }
+    if (a.o_acc) a.o_acc[r] = acc;
+    if (a.o_bgT) a.o_bgT[r] = (float)carry;                               // transmittance[:, -1] (bg_transmittance)
+    if (a.o_normal && a.normals) { a.o_normal[r * 3] = nx; a.o_normal[r * 3 + 1] = ny; a.o_normal[r * 3 + 2] = nz; }
+    if (a.o_depth && a.eu) a.o_depth[r] = dsum / (acc + 1e-10f);
+    if (a.o_minmax && a.eu && smin <= smax) { atomic_min_float(a.o_minmax, smin); atomic_max_float(a.o_minmax + 1, smax); }
+  }
+}
+
 __global__ void k_depth_clip(float* __restrict__ depth, const float* __restrict__ mm, int64_t R) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) depth[r] = fminf(fmaxf(depth[r], mm[0]), mm[1]);
@@ -175,5 +245,24 @@ extern "C" int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64
   SDFB_REQUIRE(depth && steps_minmax, "NULL pointer");
   k_depth_clip<<<(unsigned)ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>(depth, steps_minmax, n_rays);
   SDFB_LAUNCHED("k_depth_clip");
+  return 0;
+}
+
+
+extern "C" int sdfb200_render_alphas(const float* alphas, const float* rgb, const float* normals, const float* euclid_bins, const float* bg,
+                                     int32_t bg_mode, int32_t clamp01, int64_t n_rays, int32_t n_samples, float* weights, float* bg_transmittance,
+                                     const sdfb200_render_out_t* out, void* stream) {
+  SDFB_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
+  SDFB_REQUIRE(out != nullptr && alphas != nullptr, "NULL pointer");
+  if (n_rays == 0) return 0;
+  if (out->rgb) SDFB_REQUIRE(rgb != nullptr && (bg_mode == SDFB200_BG_LAST_SAMPLE || bg != nullptr), "rgb output needs rgb and background");
+  if (out->depth) SDFB_REQUIRE(euclid_bins != nullptr, "depth output needs bins");
+  if (out->normal) SDFB_REQUIRE(normals != nullptr, "normal output needs normals");
+  RenderAlphaArgs a;
+  a.alphas = alphas; a.rgb = rgb; a.normals = out->normal ? normals : nullptr; a.eu = out->depth ? euclid_bins : nullptr; a.bg = bg; a.bg_mode = bg_mode;
+  a.clamp01 = clamp01; a.R = n_rays; a.S = n_samples; a.o_weights = weights; a.o_rgb = out->rgb; a.o_depth = out->depth; a.o_normal = out->normal;
+  a.o_acc = out->accumulation; a.o_bgT = bg_transmittance; a.o_minmax = out->steps_minmax;
+  k_render_alphas<<<(unsigned)ceil_div(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(a);
+  SDFB_LAUNCHED("k_render_alphas");
   return 0;
 }

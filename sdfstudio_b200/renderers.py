@@ -12,6 +12,18 @@ from . import _lib
 from .rays import bins_of
 
 
+_MM_INIT = {}
+
+
+def _minmax_init(dev):
+    """device-resident {+inf, -inf} (cloned on the device: no host->device copy / sync per call)."""
+    t = _MM_INIT.get(str(dev))
+    if t is None:
+        t = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        _MM_INIT[str(dev)] = t
+    return t.clone()
+
+
 def _render(weights, rgb=None, normals=None, bins=None, background=None, clamp01=False, depth_method: Optional[str] = None,
             want_acc=False, want_normal=False, clip_depth=True):
     lib = _lib.load()
@@ -51,7 +63,7 @@ def _render(weights, rgb=None, normals=None, bins=None, background=None, clamp01
     if depth_method is not None:
         res["depth"] = torch.empty(R, device=dev, dtype=torch.float32)
         out.depth = res["depth"].data_ptr()
-        mm = torch.tensor([float("inf"), float("-inf")], device=dev, dtype=torch.float32)
+        mm = _minmax_init(dev)
         out.steps_minmax = mm.data_ptr()
     _lib.check(lib.sdfb200_render(_lib.ptr(w), _lib.ptr(rgb_c), _lib.ptr(nrm_c), _lib.ptr(bins), _lib.ptr(bg_t), bg_mode, int(clamp01),
                                   int(depth_method == "median"), R, S, out, _lib.stream_ptr()), "sdfb200_render")
@@ -120,3 +132,39 @@ def render_all(weights, rgb, normals, ray_samples, background, training: bool = 
     """rgb + depth + normal + accumulation in one launch (what SurfaceModel.get_outputs computes with four renderers)."""
     return _render(weights, rgb=rgb, normals=normals, bins=bins_of(ray_samples), background=background, clamp01=not training,
                    depth_method=depth_method, want_acc=True, want_normal=True)
+
+
+def render_from_alphas(alphas, rgb, normals, ray_samples, background, training: bool = False, want_weights: bool = True):
+    """alphas [R,S,1] -> weights + rgb + expected depth + normal + accumulation + bg_transmittance in ONE launch
+    (sdfb200_render_alphas): the fused form of get_weights_and_transmittance_from_alphas + the four renderers."""
+    lib = _lib.load()
+    a = _lib.f32c(alphas[..., 0])
+    R, S = a.shape
+    dev = a.device
+    rgb_c, nrm_c, bins = _lib.f32c(rgb), _lib.f32c(normals), bins_of(ray_samples)
+    bg_mode, bg_t = _lib.BG_COLOR, None
+    if isinstance(background, str):
+        if background == "last_sample":
+            bg_mode = _lib.BG_LAST_SAMPLE
+        elif background == "random":
+            bg_mode, bg_t = _lib.BG_PER_RAY, torch.rand(R, 3, device=dev)
+        else:
+            raise ValueError(f"unknown background {background!r}")
+    else:
+        bg_t = _lib.f32c(torch.as_tensor(background, dtype=torch.float32).to(dev))
+        if bg_t.dim() == 2:
+            bg_mode = _lib.BG_PER_RAY
+    res = {"rgb": torch.empty(R, 3, device=dev), "depth": torch.empty(R, device=dev), "normal": torch.empty(R, 3, device=dev),
+           "accumulation": torch.empty(R, device=dev), "bg_transmittance": torch.empty(R, device=dev)}
+    w = torch.empty(R, S, device=dev) if want_weights else None
+    mm = _minmax_init(dev)
+    out = _lib.RenderOut()
+    out.rgb, out.depth, out.normal, out.accumulation, out.steps_minmax = (res["rgb"].data_ptr(), res["depth"].data_ptr(), res["normal"].data_ptr(),
+                                                                           res["accumulation"].data_ptr(), mm.data_ptr())
+    _lib.check(lib.sdfb200_render_alphas(_lib.ptr(a), _lib.ptr(rgb_c), _lib.ptr(nrm_c), _lib.ptr(bins), _lib.ptr(bg_t), bg_mode, int(not training), R, S,
+                                         _lib.ptr(w), res["bg_transmittance"].data_ptr(), out, _lib.stream_ptr()), "sdfb200_render_alphas")
+    _lib.check(lib.sdfb200_depth_clip(out.depth, out.steps_minmax, R, _lib.stream_ptr()), "sdfb200_depth_clip")
+    res["depth"], res["accumulation"], res["bg_transmittance"] = res["depth"][:, None], res["accumulation"][:, None], res["bg_transmittance"][:, None]
+    if want_weights:
+        res["weights"] = w[..., None]
+    return res

@@ -155,6 +155,11 @@ def test_weights_and_renderers_match_reference_golden(name):
     assert torch.equal(sb.DepthRenderer("median")(w, RS()), G["render_depth_median"])
     close(sb.AccumulationRenderer()(w), G["render_acc"])
     close(sb.SemanticRenderer()(G["normals"], w), G["render_normal"])
+    fused = sb.render_from_alphas(G["alphas"], G["rgb"], G["normals"], RS(), torch.ones(3, device="cuda"))
+    torch.testing.assert_close(fused["weights"], G["weights_alpha"], rtol=2e-6, atol=1e-9)
+    torch.testing.assert_close(fused["bg_transmittance"], G["trans_alpha"][:, -1], rtol=2e-6, atol=1e-9)
+    for k, gk in (("rgb", "render_rgb_white"), ("depth", "render_depth_expected"), ("normal", "render_normal"), ("accumulation", "render_acc")):
+        close(fused[k], G[gk])
     allr = sb.render_all(w, G["rgb"], G["normals"], RS(), torch.ones(3))
     close(allr["rgb"], G["render_rgb_white"])
     close(allr["depth"], G["render_depth_expected"])

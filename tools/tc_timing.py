@@ -30,7 +30,7 @@ with torch.no_grad():
 torch.cuda.synchronize()
 buf = (ctypes.c_longlong * 512)()
 sb._lib.check(sb._lib.load().sdfb200_debug_tc_timing(buf))
-names = ["encode", "wait G0", "E0", "wait G1", "E1", "wait G2", "E2", "wait B1", "EB1", "wait B0", "EB0+cin", "wait C0", "EC0", "wait C1", "EC1+heads"]
+names = ["start", "wait G0", "E0", "wait G1", "E1", "slice2", "-", "wait B1", "EB1", "wait B0", "EB0", "wait C0", "EC0", "wait C1", "EC1+heads"]
 for t in (1, 2, 5, 10):
     st = [buf[t * 32 + k] for k in range(16)]
     tot = st[15] - st[0]
