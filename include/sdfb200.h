@@ -159,6 +159,18 @@ int sdfb200_field_forward(const sdfb200_field_t* f, const void* packed, const vo
                           const sdfb200_field_out_t* out, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Proposal density field.  Replaces HashMLPDensityField.get_density / density_fn (nerfstudio/fields/density_fields.py:40-121,
+ * fields/base_field.py:48-65): tcnn.NetworkWithInputEncoding (HashGrid -> FullyFusedMLP, ReLU, no biases) + trunc_exp
+ * (field_components/activations.py:24-42).  positions [n,3]; normalisation: aabb != NULL -> (x - aabb[0]) / (aabb[1] - aabb[0])
+ * (data/scene_box.py:67-76), else SceneContraction (`contraction`) followed by (x + 2) / 4.
+ * weights (fp32, row-major): [hidden, in_pad] | (n_hidden_layers-1) x [hidden, hidden] | [hidden]; in_pad = L*F rounded up to 16.
+ * density [n] = exp(pre-activation); pre_activation [n] optional.
+ * ------------------------------------------------------------------------------------------------------------- */
+int sdfb200_density_field_forward(const sdfb200_grid_t* grid, const void* table, const float* weights, int32_t hidden_dim,
+                                  int32_t n_hidden_layers, int32_t contraction, const float* aabb, const float* positions,
+                                  int64_t n, float* density, float* pre_activation, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Ray samplers.  Replace nerfstudio/model_components/ray_samplers.py.  A sample set is a pair of bin-edge buffers
  * [R, S+1]: `spacing` (normalised) and `euclid` (distance along the ray), cf. cameras/rays.py:295-339.
  * ------------------------------------------------------------------------------------------------------------- */

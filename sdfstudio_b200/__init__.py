@@ -9,6 +9,7 @@ Host side mirrors the reference's plug points:
 All arithmetic runs in libsdfb200.so (CUDA, sm_100a) behind the C ABI of include/sdfb200.h.  No CPU / PyTorch fallback.
 """
 from . import _lib  # noqa: F401
+from .density_fields import HashMLPDensityField  # noqa: F401
 from .encoding import Encoding, HashEncoding  # noqa: F401
 from .field_heads import FieldHeadNames  # noqa: F401
 from .rays import Frustums, RayBundle, RaySamples  # noqa: F401

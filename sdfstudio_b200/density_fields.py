@@ -1,0 +1,110 @@
+"""B200-native drop-in for ``nerfstudio.fields.density_fields.HashMLPDensityField`` (the proposal networks of
+neus-facto / bakedsdf, density_fields.py:40-121): same constructor, ``get_density``, ``density_fn``.  The reference builds a
+``tcnn.NetworkWithInputEncoding`` (HashGrid + FullyFusedMLP, ReLU, no biases, output activation None) and applies
+``trunc_exp``; here one fused kernel (sdfb200_density_field_forward) does lookup + MLP + exp.
+
+Parameters: ``mlp_base.params`` is ONE flat fp32 tensor like tcnn's: network weights first ([hidden, in_pad], hidden x hidden
+blocks, [hidden] output row; in_pad = L*F rounded up to 16), then the grid table in tcnn level layout.  tiny-cuda-nn is not
+vendored in the reference, so bit-compatibility of this ordering with a tcnn checkpoint is UNPINNED.
+"""
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .encoding import make_grid_desc
+
+
+class _NetworkWithInputEncoding(nn.Module):
+    def __init__(self, n_levels, n_features, log2_hashmap_size, base_res, per_level_scale, hidden_dim, n_hidden_layers, seed=1337):
+        super().__init__()
+        self.hidden_dim, self.n_hidden_layers = hidden_dim, n_hidden_layers
+        self.in_dim = n_levels * n_features
+        self.in_pad = (self.in_dim + 15) // 16 * 16
+        self.desc = make_grid_desc("tcnn", n_levels, n_features, log2_hashmap_size, base_res, per_level_scale, False)
+        self.n_net = hidden_dim * self.in_pad + (n_hidden_layers - 1) * hidden_dim * hidden_dim + hidden_dim
+        self.n_grid = self.desc._total_entries * n_features
+        g = torch.Generator().manual_seed(seed)
+        # tcnn: xavier-uniform weights, U(-1e-4, 1e-4) grid
+        w0 = (torch.rand(hidden_dim, self.in_pad, generator=g) * 2 - 1) * math.sqrt(6.0 / (self.in_pad + hidden_dim))
+        w0[:, self.in_dim:] = 0.0
+        ws = [w0.reshape(-1)]
+        for _ in range(n_hidden_layers - 1):
+            ws.append(((torch.rand(hidden_dim, hidden_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (2 * hidden_dim))).reshape(-1))
+        ws.append((torch.rand(hidden_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (hidden_dim + 16)))
+        grid = (torch.rand(self.n_grid, generator=g) * 2 - 1) * 1e-4
+        self.params = nn.Parameter(torch.cat(ws + [grid]))
+
+    @property
+    def weights(self):
+        return self.params[: self.n_net]
+
+    @property
+    def table(self):
+        return self.params[self.n_net:]
+
+
+class HashMLPDensityField(nn.Module):
+    """density_fields.py:40-121."""
+
+    def __init__(self, aabb, num_layers: int = 2, hidden_dim: int = 64, spatial_distortion=None, use_linear=False, num_levels=8, max_res=1024,
+                 base_res=16, log2_hashmap_size=18, features_per_level=2) -> None:
+        super().__init__()
+        if use_linear:
+            raise NotImplementedError("use_linear=True (encoding + nn.Linear) is not used by any SDF preset")
+        if hidden_dim not in (16, 32, 64):
+            raise NotImplementedError("hidden_dim must be 16, 32 or 64")
+        self.aabb = nn.Parameter(torch.as_tensor(aabb, dtype=torch.float32), requires_grad=False)
+        self.spatial_distortion = spatial_distortion
+        self.use_linear = use_linear
+        growth = float(np.exp((np.log(max_res) - np.log(base_res)) / (num_levels - 1)))
+        self.mlp_base = _NetworkWithInputEncoding(num_levels, features_per_level, log2_hashmap_size, base_res, growth, hidden_dim, num_layers - 1)
+
+    def _contraction_code(self):
+        sd = self.spatial_distortion
+        if sd is None:
+            return None
+        order = getattr(sd, "order", None)
+        if order is None:
+            return _lib.CONTRACT_L2
+        if order == float("inf"):
+            return _lib.CONTRACT_LINF
+        raise NotImplementedError(f"SceneContraction order {order!r}")
+
+    def density_from_positions(self, positions: torch.Tensor, return_pre_activation: bool = False):
+        """positions [..., 3] -> density [..., 1] (fields/base_field.py:48-65 + density_fields.py:98-118)."""
+        if torch.is_grad_enabled() and self.training and self.mlp_base.params.requires_grad:
+            raise NotImplementedError("sdfstudio_b200.HashMLPDensityField: the differentiable (training) path is not in this build")
+        lib = _lib.load()
+        pos = _lib.f32c(positions.reshape(-1, 3))
+        n = pos.shape[0]
+        dens = torch.empty(n, device=pos.device, dtype=torch.float32)
+        pre = torch.empty_like(dens) if return_pre_activation else None
+        code = self._contraction_code()
+        aabb = None if code is not None else _lib.f32c(self.aabb.detach())
+        nb = self.mlp_base
+        p = nb.params.detach()
+        w, table = p[: nb.n_net], p[nb.n_net:]
+        desc = nb.desc
+        desc.active_levels = desc.n_levels
+        desc.table_dtype = _lib.DT_F32
+        _lib.check(lib.sdfb200_density_field_forward(desc, table.data_ptr(), w.data_ptr(), nb.hidden_dim, nb.n_hidden_layers, code or 0, _lib.ptr(aabb),
+                                                     _lib.ptr(pos), n, _lib.ptr(dens), _lib.ptr(pre), _lib.stream_ptr()), "sdfb200_density_field_forward")
+        dens = dens.view(*positions.shape[:-1], 1)
+        return (dens, pre.view(*positions.shape[:-1], 1)) if return_pre_activation else dens
+
+    def density_fn(self, positions: torch.Tensor) -> torch.Tensor:
+        return self.density_from_positions(positions)
+
+    def get_density(self, ray_samples):
+        return self.density_from_positions(ray_samples.frustums.get_positions()), None
+
+    def get_outputs(self, ray_samples, density_embedding: Optional[torch.Tensor] = None):
+        return {}
+
+    def forward(self, ray_samples):
+        density, _ = self.get_density(ray_samples)
+        return {"density": density}

@@ -346,3 +346,72 @@ def test_large_batch_crosses_chunks():
     small = field(sb.UniformSampler(num_samples=S).eval()(rb2), return_alphas=True)
     for k in (sb.FieldHeadNames.RGB, sb.FieldHeadNames.SDF, sb.FieldHeadNames.ALPHA, sb.FieldHeadNames.GRADIENT):
         assert torch.equal(big[k][sl], small[k]), k
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# proposal density field + ProposalNetworkSampler
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("hidden,layers,contraction", [(16, 2, None), (64, 3, "linf"), (32, 2, "l2")])
+def test_density_field_matches_oracle(hidden, layers, contraction):
+    import sdfstudio_b200 as sb
+    from oracle import density as odensity
+
+    class _C:
+        def __init__(self, order):
+            self.order = order
+
+    sd = None if contraction is None else _C(float("inf") if contraction == "linf" else None)
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    f = sb.HashMLPDensityField(aabb, num_layers=layers, hidden_dim=hidden, spatial_distortion=sd, num_levels=5, max_res=256, log2_hashmap_size=12).cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    with torch.no_grad():
+        nb = f.mlp_base
+        nb.params[nb.n_net:] = ((torch.rand(nb.n_grid, generator=g) * 2 - 1) * 0.5).cuda()
+    pos = (torch.rand(37, 11, 3, generator=g) * 2 - 1) * (3.0 if contraction else 1.0)
+    dens, pre = f.density_from_positions(pos.cuda(), return_pre_activation=True)
+    p = f.mlp_base.params.detach().cpu()
+    growth = hashgrid.growth_factor(5, 16, 256)
+    od, opre = odensity.density_field(pos, p[: nb.n_net], p[nb.n_net:], hidden, layers - 1, 5, 2, 12, 16, growth,
+                                      aabb=None if contraction else aabb, contraction=contraction)
+    assert dens.shape == (37, 11, 1)
+    torch.testing.assert_close(pre.cpu(), opre, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dens.cpu(), od, rtol=1e-4, atol=1e-6)
+
+
+def test_proposal_network_sampler_matches_oracle():
+    """neus-facto's sampler (ray_samplers.py:537-578 with the preset numbers neus_facto.py:47-64): (256, 96) proposal samples
+    through two HashMLPDensityFields, 48 final samples -- this library end to end vs the CPU oracle."""
+    import numpy as np
+
+    import sdfstudio_b200 as sb
+    from oracle import density as odensity
+
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    g = torch.Generator().manual_seed(9)
+    nets = []
+    for max_res in (64, 256):
+        f = sb.HashMLPDensityField(aabb, num_layers=2, hidden_dim=16, num_levels=5, max_res=max_res, log2_hashmap_size=17).cuda().eval()
+        with torch.no_grad():
+            nb = f.mlp_base
+            nb.params[nb.n_net:] = ((torch.rand(nb.n_grid, generator=g) * 2 - 1) * 2.0).cuda()
+        nets.append(f)
+    R = 200
+    o, d, cam = cases.synthetic_rays(R, 77)
+    nears, fars = torch.full((R, 1), 0.5), torch.full((R, 1), 4.5)
+    rb = make_bundle(o, d, cam, nears, fars)
+    sampler = sb.ProposalNetworkSampler(num_proposal_samples_per_ray=(256, 96), num_nerf_samples_per_ray=48, num_proposal_network_iterations=2).eval()
+    rs, weights_list, rs_list = sampler(rb, density_fns=[n.density_fn for n in nets])
+    assert sb.rays.bins_of(rs).shape == (R, 49) and len(weights_list) == 2
+
+    def ofn(net, max_res):
+        nb = net.mlp_base
+        p = nb.params.detach().cpu()
+        gf = float(np.exp((np.log(max_res) - np.log(16)) / 4))
+        return lambda pos: odensity.density_field(pos, p[: nb.n_net], p[nb.n_net:], 16, 1, 5, 2, 17, 16, gf, aabb=aabb)[0][..., 0]
+
+    ob, owl, obl = samplers.proposal_sampler(o, d, nears, fars, [ofn(nets[0], 64), ofn(nets[1], 256)], (256, 96), 48)
+    torch.testing.assert_close(weights_list[0][..., 0].cpu(), owl[0], rtol=2e-4, atol=1e-6)
+    # sample positions: inverse-CDF conditioning -> compare at the level of the oracle's own sensitivity
+    torch.testing.assert_close(sb.rays.bins_of(rs_list[1]).cpu(), obl[1].euclid, rtol=0, atol=5e-3)
+    torch.testing.assert_close(sb.rays.bins_of(rs).cpu(), ob.euclid, rtol=0, atol=2e-2)
+    assert (sb.rays.bins_of(rs)[:, 1:] >= sb.rays.bins_of(rs)[:, :-1]).all()
