@@ -34,7 +34,7 @@ FLOP_PER_SAMPLE = 763904  # 381 952 MAC (geo 149 504 + gra
 WORKLOAD = "neus-facto-dtu65-4096x128"
 
 
-def make_field(device, precision="fp32", seed=0):
+def make_field(device, precision="fp32", seed=0, table_dtype="fp32"):
     """The product SDFField for the workload (neus-facto preset, method_configs.py:472-480 + README override
     inside_outside=False), random-init + perturbation so that hash + PE inputs matter."""
     import sdfstudio_b200 as sb
@@ -42,7 +42,7 @@ def make_field(device, precision="fp32", seed=0):
 
     torch.manual_seed(seed)
     cfg = sb.SDFFieldConfig(use_grid_feature=True, num_layers=2, num_layers_color=2, hidden_dim=256, bias=0.5, beta_init=0.3,
-                            use_appearance_embedding=False, inside_outside=False, grid_layout="torch", precision=precision)
+                            use_appearance_embedding=False, inside_outside=False, grid_layout="torch", precision=precision, table_dtype=table_dtype)
     field = sb.SDFField(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=49)
     perturb_field_(field, seed)
     return field.to(device).eval()
@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SDFB200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table-dtype", default="fp32", choices=["fp32", "fp16"], help="fp16 = gather from a half-precision copy (tiny-cuda-nn's storage)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -218,7 +219,7 @@ def main():
     precision = args.precision
     if precision == "auto":
         precision = "bf16x3"   # tcgen05 path at parity-grade precision (bf16 split, fp32 accumulate); fp32 / bf16 via --precision
-    field = make_field(dev, precision)
+    field = make_field(dev, precision, table_dtype=args.table_dtype)
     sampler = sb.UniformSampler(num_samples=S).eval()
     white = torch.ones(3, device=dev)
     H = sb.FieldHeadNames
@@ -315,7 +316,7 @@ def main():
             "metric": "rays/sec at 4096 rays x 128 samples", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (fp32 accumulate)", "bf16": "bf16 (fp32 accumulate)"}[precision], "data": "synthetic",
-            "config": {"workload": WORKLOAD, "rays_per_gpu": R_PER_GPU, "samples_per_ray": S, "sampler": "UniformSampler(128), eval", "field": "neus-facto SDFField L16 F2 T2^19 MLP 2x256 (torch-layout table)",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": R_PER_GPU, "samples_per_ray": S, "sampler": "UniformSampler(128), eval", "field": f"neus-facto SDFField L16 F2 T2^19 MLP 2x256 (torch-layout table, {args.table_dtype})",
                        "precision": precision, "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"ray-shard x{world}, no data-path collective"},
             "e2e": {"value": e2e, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),

@@ -1,5 +1,5 @@
 // Fused tcgen05 evaluation of the SDF field (SDFB200_PRECISION_BF16X3 / _BF16) for the neus-facto family of shapes:
-// geo MLP in-256-256-(1+256), colour MLP cin-256-256-3, analytic d sdf/dx, 2-feature fp32 hash grid.
+// geo MLP in-256-256-(1+256), colour MLP cin-256-256-3, analytic d sdf/dx, 2-feature hash grid (fp32 or fp16 table).
 //
 // One persistent CTA per SM walks 128-point tiles.  Per tile (everything stays on chip except two L2-resident spills):
 //   encode   16 epilogue warps: position, contraction, PE, hash gathers (+ jacobian) -> bf16 split planes in smem
@@ -204,7 +204,8 @@ __device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slic
       float dj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       if (a.use_grid && l < a.grid.active_levels) {
         const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;
-        encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
+        if (a.grid.table_dtype == SDFB200_DT_F16) encode_level<__half, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
+        else encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
       }
 #pragma unroll
       for (int f = 0; f < 2; ++f) {
@@ -764,7 +765,7 @@ bool field_tc_supported(const sdfb200_field_t& f, const FieldPlan& p) {
   if (p.geo[0].N != 256 || p.geo[1].N != 256 || p.geo_feat != 256 || p.col[0].N != 256 || p.col[1].N != 256) return false;
   if (f.use_numerical_gradients || f.off_axis || f.use_diffuse_color || f.use_specular_tint || f.use_reflections) return false;
   if (p.in_dim > kInK || p.grid_dim > kMaxGridDim || p.pe_dim > kMaxPe) return false;
-  if (f.use_grid_feature && (f.grid.n_features != 2 || f.grid.table_dtype != SDFB200_DT_F32)) return false;
+  if (f.use_grid_feature && f.grid.n_features != 2) return false;
   const int cm = 3 + 27 + 3 + f.appearance_dim + (f.use_n_dot_v ? 1 : 0);
   if (38 + f.appearance_dim > kInK) return false;
   return true;

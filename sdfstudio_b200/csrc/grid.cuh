@@ -78,13 +78,20 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
   return p;
 }
-// thread-local policy used by TableLoad when the caller opted in (0 = plain loads)
-struct TablePolicy { uint64_t pol; };
-template <int F>
-__device__ __forceinline__ void table_load_f32_hint(const void* table, uint64_t row, float (&v)[F], uint64_t pol) {
+// hinted F=2 table loads (fp32: 8 bytes, fp16: 4 bytes) used by the fused kernel
+template <typename T, int F>
+__device__ __forceinline__ void table_load_hint(const void* table, uint64_t row, float (&v)[F], uint64_t pol) {
   static_assert(F == 2, "hinted loads are only used by the F=2 fused kernel");
-  const float* p = reinterpret_cast<const float*>(table) + row * F;
-  asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v[0]), "=f"(v[1]) : "l"(p), "l"(pol));
+  if constexpr (sizeof(T) == 4) {
+    const float* p = reinterpret_cast<const float*>(table) + row * F;
+    asm volatile("ld.global.nc.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;" : "=f"(v[0]), "=f"(v[1]) : "l"(p), "l"(pol));
+  } else {
+    const __half* p = reinterpret_cast<const __half*>(table) + row * F;
+    uint32_t raw;
+    asm volatile("ld.global.nc.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(raw) : "l"(p), "l"(pol));
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&raw));
+    v[0] = t.x; v[1] = t.y;
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -114,14 +121,14 @@ __device__ __forceinline__ void encode_level_torch(const sdfb200_grid_t& g, cons
   // hash = x ^ y*P1 ^ z*P2 (int64 in the reference; the low log2T bits equal the uint32 product's low bits)
   const uint32_t hyc = cy * kPrimeY, hyf = fy * kPrimeY, hzc = cz * kPrimeZ, hzf = fz * kPrimeZ;
   float f0[F], f1[F], f2[F], f3[F], f4[F], f5[F], f6[F], f7[F];
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyc ^ hzc) & mask), f0, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzc) & mask), f0);  // (c,c,c)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyf ^ hzc) & mask), f1, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzc) & mask), f1);  // (c,f,c)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyf ^ hzc) & mask), f2, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzc) & mask), f2);  // (f,f,c)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyc ^ hzc) & mask), f3, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzc) & mask), f3);  // (f,c,c)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyc ^ hzf) & mask), f4, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzf) & mask), f4);  // (c,c,f)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((cx ^ hyf ^ hzf) & mask), f5, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzf) & mask), f5);  // (c,f,f)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyf ^ hzf) & mask), f6, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzf) & mask), f6);  // (f,f,f)
-  if constexpr (HINT) table_load_f32_hint<F>(table, base + ((fx ^ hyc ^ hzf) & mask), f7, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzf) & mask), f7);  // (f,c,f)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((cx ^ hyc ^ hzc) & mask), f0, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzc) & mask), f0);  // (c,c,c)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((cx ^ hyf ^ hzc) & mask), f1, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzc) & mask), f1);  // (c,f,c)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((fx ^ hyf ^ hzc) & mask), f2, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzc) & mask), f2);  // (f,f,c)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((fx ^ hyc ^ hzc) & mask), f3, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzc) & mask), f3);  // (f,c,c)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((cx ^ hyc ^ hzf) & mask), f4, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyc ^ hzf) & mask), f4);  // (c,c,f)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((cx ^ hyf ^ hzf) & mask), f5, pol); else TableLoad<T, F>::load(table, base + ((cx ^ hyf ^ hzf) & mask), f5);  // (c,f,f)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((fx ^ hyf ^ hzf) & mask), f6, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyf ^ hzf) & mask), f6);  // (f,f,f)
+  if constexpr (HINT) table_load_hint<T, F>(table, base + ((fx ^ hyc ^ hzf) & mask), f7, pol); else TableLoad<T, F>::load(table, base + ((fx ^ hyc ^ hzf) & mask), f7);  // (f,c,f)
   const float nx = __fsub_rn(1.f, ox), ny = __fsub_rn(1.f, oy), nz = __fsub_rn(1.f, oz);
 #pragma unroll
   for (int f = 0; f < F; ++f) {
@@ -179,7 +186,7 @@ __device__ __forceinline__ void encode_level_tcnn(const sdfb200_grid_t& g, const
     uint32_t idx = hashed ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
     idx %= size;
     float v[F];
-    if constexpr (HINT) table_load_f32_hint<F>(table, base + idx, v, pol); else TableLoad<T, F>::load(table, base + idx, v);
+    if constexpr (HINT) table_load_hint<T, F>(table, base + idx, v, pol); else TableLoad<T, F>::load(table, base + idx, v);
     const float wt = wx * wy * wz;
 #pragma unroll
     for (int f = 0; f < F; ++f) {

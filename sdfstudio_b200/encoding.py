@@ -84,7 +84,7 @@ class _GridEncodeFn(torch.autograd.Function):
         x = _lib.f32c(x)
         n = x.shape[0]
         out = torch.empty(n, enc.n_output_dims, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sdfb200_grid_encode(enc._desc_ref(), _lib.ptr(table), _lib.ptr(x), n, _lib.ptr(out), enc.n_output_dims, None,
+        _lib.check(lib.sdfb200_grid_encode(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), n, _lib.ptr(out), enc.n_output_dims, None,
                                            _lib.stream_ptr()), "sdfb200_grid_encode")
         ctx.save_for_backward(x, table)
         ctx.enc = enc
@@ -100,7 +100,7 @@ class _GridEncodeFn(torch.autograd.Function):
         n = x.shape[0]
         dtable = torch.zeros(table.shape, device=table.device, dtype=torch.float32)
         dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
-        _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(table), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
+        _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
                                                     _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
         return dx, dtable.to(table.dtype), None
 
@@ -109,8 +109,15 @@ class Encoding(nn.Module):
     """``tinycudann.Encoding`` look-alike (HashGrid / DenseGrid otypes)."""
 
     def __init__(self, n_input_dims: int, encoding_config: dict, seed: int = 1337, dtype: Optional[torch.dtype] = None,
-                 layout: str = "tcnn", device: Optional[torch.device] = None):
+                 layout: str = "tcnn", device: Optional[torch.device] = None, table_dtype: str = "fp32"):
         super().__init__()
+        if table_dtype not in ("fp32", "fp16"):
+            raise ValueError("table_dtype must be 'fp32' or 'fp16'")
+        # "fp16": the kernels gather from a half-precision copy of the (fp32 master) parameters, which is what tiny-cuda-nn
+        # itself does (fp16 compute params + fp32 master); the copy is refreshed whenever the parameter changes
+        self.table_dtype = table_dtype
+        self._half_cache = None
+        self._half_key = None
         if n_input_dims != 3:
             raise ValueError("only 3-D grids are supported")
         otype = encoding_config.get("otype", "HashGrid")
@@ -146,9 +153,21 @@ class Encoding(nn.Module):
     def table(self) -> torch.Tensor:
         return self.hash_table if self.layout == "torch" else self.params
 
+    def compute_table(self) -> torch.Tensor:
+        """the tensor the kernels gather from (the parameter itself, or its cached fp16 copy)."""
+        t = self.table
+        if self.table_dtype == "fp32" or t.dtype == torch.float16:
+            return t.detach()
+        key = (t.data_ptr(), t._version, str(t.device))
+        if self._half_key != key:
+            self._half_cache = t.detach().to(torch.float16)
+            self._half_key = key
+        return self._half_cache
+
     def _desc_ref(self):
         self._desc.active_levels = int(self.active_levels)
-        self._desc.table_dtype = _lib.DT_F16 if self.table.dtype == torch.float16 else _lib.DT_F32
+        half = self.table_dtype == "fp16" or self.table.dtype == torch.float16
+        self._desc.table_dtype = _lib.DT_F16 if half else _lib.DT_F32
         return self._desc
 
     def set_active_levels(self, levels: int):

@@ -119,6 +119,7 @@ class SDFFieldConfig:
     # ---- B200 knobs (not in the reference) ----
     grid_layout: str = "tcnn"      # "tcnn" (checkpoint compatible) | "torch" (reference HashEncoding layout)
     precision: str = "fp32"        # "fp32" | "bf16x3" | "bf16"   (include/sdfb200.h SDFB200_PRECISION_*)
+    table_dtype: str = "fp32"      # "fp32" | "fp16": gather from an fp16 copy of the table (tiny-cuda-nn's own storage precision)
 
     def setup(self, **kwargs):
         return self._target(self, **kwargs)
@@ -151,6 +152,7 @@ class SDFField(nn.Module):
                 "interpolation": "Smoothstep" if config.hash_smoothstep else "Linear",
             },  # fmt: skip
             layout=getattr(config, "grid_layout", "tcnn"),
+            table_dtype=getattr(config, "table_dtype", "fp32"),
         )
         self.hash_encoding_mask = torch.ones(self.num_levels * self.features_per_level, dtype=torch.float32)
         self._active_levels = self.num_levels
@@ -376,7 +378,7 @@ class SDFField(nn.Module):
         fout = _lib.FieldOut()
         for k, t in outs.items():
             setattr(fout, k, t.data_ptr())
-        table = self.encoding.table.detach() if self.use_grid_feature else None
+        table = self.encoding.compute_table() if self.use_grid_feature else None
         _lib.check(lib.sdfb200_field_forward(desc, _lib.ptr(packed), _lib.ptr(table), fin, fout, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
                    "sdfb200_field_forward")
         return outs

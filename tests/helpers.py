@@ -14,7 +14,7 @@ def load_golden(name, device="cpu"):
     return {k: torch.from_numpy(v).to(device) for k, v in np.load(os.path.join(GOLDEN_DIR, name + ".npz")).items()}
 
 
-def product_field(spec: FieldSpec, params, kw, device="cuda", precision="fp32"):
+def product_field(spec: FieldSpec, params, kw, device="cuda", precision="fp32", table_dtype="fp32"):
     """sdfstudio_b200.SDFField with the oracle's seeded parameters loaded (names match the reference state_dict)."""
     import sdfstudio_b200 as sb
 
@@ -27,7 +27,7 @@ def product_field(spec: FieldSpec, params, kw, device="cuda", precision="fp32"):
         use_n_dot_v=spec.use_n_dot_v, rgb_padding=spec.rgb_padding, off_axis=spec.off_axis, use_numerical_gradients=spec.use_numerical_gradients,
         num_levels=spec.num_levels, max_res=spec.max_res, base_res=spec.base_res, log2_hashmap_size=spec.log2_hashmap_size,
         hash_features_per_level=spec.hash_features_per_level, hash_smoothstep=spec.hash_smoothstep, use_position_encoding=spec.use_position_encoding,
-        grid_layout=spec.grid_layout, precision=precision,
+        grid_layout=spec.grid_layout, precision=precision, table_dtype=table_dtype,
     )  # fmt: skip
 
     class _Contraction:  # duck-typed SceneContraction (only `.order` is read)
@@ -58,15 +58,17 @@ def product_field(spec: FieldSpec, params, kw, device="cuda", precision="fp32"):
     return f
 
 
-def build_case(name, device="cuda", precision="fp32"):
+def build_case(name, device="cuda", precision="fp32", table_dtype="fp32"):
     spec, kw, o, d, cam, nears, fars = cases.case_inputs(name)
     params = init_params(spec, **cases.init_kwargs(kw))
+    if table_dtype == "fp16" and "hash_table" in params:
+        params["hash_table"] = params["hash_table"].half().float()   # the model IS the fp16-representable table (tcnn semantics)
     oracle = OracleField(spec, params)
     if "mask_level" in kw:
         oracle.update_mask(kw["mask_level"])
     if "num_grad_delta" in kw:
         oracle.numerical_gradients_delta = kw["num_grad_delta"]
-    field = product_field(spec, params, kw, device, precision)
+    field = product_field(spec, params, kw, device, precision, table_dtype)
     return spec, kw, o, d, cam, nears, fars, oracle, field
 
 

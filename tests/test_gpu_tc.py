@@ -112,3 +112,23 @@ def test_field_tc_ragged_tail_and_point_mode():
     oo = oracle.get_outputs(o[:37], d[:37], ob.starts, ob.deltas, cam[:37], return_alphas=True)
     assert rel_err(out[sb.FieldHeadNames.RGB], oo["rgb"], 1e-2) < 1e-3
     assert rel_err(out[sb.FieldHeadNames.SDF], oo["sdf"], 1e-3) < 1e-3
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_field_fp16_table_matches_oracle_on_the_same_quantised_table(precision):
+    """table_dtype="fp16" (tiny-cuda-nn's storage precision): the kernels gather half-precision entries; against the oracle
+    holding the same fp16-representable values the field must agree as tightly as with an fp32 table."""
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case("neusfacto_c1", precision=precision, table_dtype="fp16")
+    assert field.encoding.compute_table().dtype == torch.float16
+    rb = make_bundle(o, d, cam, nears, fars)
+    rs = sb.UniformSampler(num_samples=kw["S"]).eval()(rb)
+    out = field(rs, return_alphas=True)
+    eu = sb.rays.bins_of(rs).cpu()
+    oo = oracle.get_outputs(o, d, eu[:, :-1], eu[:, 1:] - eu[:, :-1], cam, return_alphas=True)
+    H = sb.FieldHeadNames
+    o64 = oracle64(spec, oracle.p, kw)
+    e64 = o64.get_outputs(o.double(), d.double(), eu[:, :-1].double(), (eu[:, 1:] - eu[:, :-1]).double(), cam, return_alphas=True)
+    for key, k in ((H.SDF, "sdf"), (H.RGB, "rgb"), (H.ALPHA, "alphas"), (H.GRADIENT, "gradients")):
+        assert_within_noise(out[key], oo[k], e64[k], f"fp16-table/{precision}/{k}", factor=4.0, floor=1e-4 * float(e64[k].abs().max()))
