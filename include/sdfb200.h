@@ -80,6 +80,13 @@ int sdfb200_grid_encode(const sdfb200_grid_t* grid, const void* table, const flo
 int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
                                  int64_t n, float* dtable, float* dx01, void* stream);
 
+/* backward of sdfb200_grid_encode_backward's dx01 output (second order; what autograd's create_graph=True gives the
+ * reference for the eikonal loss, models/base_surface_model.py:358-362 through sdf_field.py:655-662).
+ * g_dx01 [n,3] = dLoss/d(dx01).  Outputs (each may be NULL): g_dout [n, L*F] (overwritten), g_table (fp32, table row
+ * layout, atomically ACCUMULATED -- zero it first), g_x01 [n,3] (ACCUMULATED). */
+int sdfb200_grid_encode_backward_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
+                                          const float* g_dx01, int64_t n, float* g_dout, float* g_table, float* g_x01, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * SDFField.  Replaces nerfstudio/fields/sdf_field.py: forward_geonetwork :380-410, gradient :424-465, get_alpha
  * :476-525, get_colors :532-612, get_outputs :614-689, LaplaceDensity :57-66, get_occupancy :527-530,
@@ -256,6 +263,21 @@ int sdfb200_render_alphas(const float* alphas, const float* rgb, const float* no
                           float* weights, float* bg_transmittance, const sdfb200_render_out_t* out, void* stream);
 /* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
 int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
+
+/* Training path: backward of sdfb200_render (expected depth) / sdfb200_render_alphas' compositing w.r.t. the per-sample
+ * inputs (autograd over renderers.py:42-295 in the reference).  `accumulation`, `depth` = forward outputs (depth BEFORE the
+ * global clip).  g_rgb [R,3], g_depth [R], g_normal [R,3], g_accumulation [R], g_weights_in [R,S]: incoming gradients, each
+ * may be NULL.  Outputs: g_weights [R,S] (required), g_rgb_samples / g_normal_samples [R,S,3] (may be NULL). */
+int sdfb200_render_backward(const float* weights, const float* rgb, const float* normals, const float* euclid_bins, const float* bg,
+                            int32_t bg_mode, int64_t n_rays, int32_t n_samples, const float* accumulation, const float* depth,
+                            const float* g_rgb, const float* g_depth, const float* g_normal, const float* g_accumulation,
+                            const float* g_weights_in, float* g_weights, float* g_rgb_samples, float* g_normal_samples, void* stream);
+
+/* backward of sdfb200_weights_from_alphas (from_density = 0; g_last_transmittance [R] = gradient of transmittance[:, -1],
+ * may be NULL) or sdfb200_weights_from_density (from_density = 1): g_weights [R,S] -> g_in [R,S]. */
+int sdfb200_weights_backward(const float* alphas_or_density, const float* euclid_bins, int32_t from_density, int64_t n_rays,
+                             int32_t n_samples, const float* g_weights, const float* g_last_transmittance, float* g_in, void* stream);
+
 
 /* ---------------------------------------------------------------------------------------------------------------*/
 int sdfb200_version(void);

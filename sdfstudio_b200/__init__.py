@@ -18,6 +18,7 @@ from .ray_samplers import (  # noqa: F401
     SqrtSampler, UniformLinDispPiecewiseSampler, UniformSampler, UniSurfSampler,
 )
 from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, SemanticRenderer, render_all, render_from_alphas  # noqa: F401
+from .spatial_distortions import SceneContraction  # noqa: F401
 from .sdf_field import LaplaceDensity, SDFField, SDFFieldConfig, SingleVarianceNetwork  # noqa: F401
 
 __version__ = "0.1.0"

@@ -215,4 +215,53 @@ __device__ __forceinline__ void encode_level(const sdfb200_grid_t& g, const void
     encode_level_tcnn<T, F, GRAD, HINT>(g, table, l, x, y, z, out, dout, pol);
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Layout-independent per-level geometry for the derivative kernels: per axis the two corner coordinates (c[d][1] carries
+// weight w[d], c[d][0] carries 1-w[d]) and w, dw/dx01, d2w/dx01^2 (piecewise: floor/ceil are treated as constants).
+// -----------------------------------------------------------------------------------------------------------------
+struct LevelGeom {
+  uint32_t c[3][2];
+  float w[3], dw[3], d2w[3];
+};
+
+__device__ __forceinline__ void level_geom(const sdfb200_grid_t& g, int l, const float (&x)[3], LevelGeom& q) {
+  const float s = g.scale[l];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    float t;
+    if (g.layout == SDFB200_GRID_TORCH) {
+      const float sx = __fmul_rn(x[d], s);
+      const float fl = floorf(sx);
+      q.c[d][0] = (uint32_t)(int)fl;
+      q.c[d][1] = (uint32_t)(int)ceilf(sx);
+      t = sx - fl;
+    } else {
+      const float p = fmaf(x[d], s, 0.5f);
+      const float fl = floorf(p);
+      q.c[d][0] = (uint32_t)(int)fl;
+      q.c[d][1] = q.c[d][0] + 1u;
+      t = p - fl;
+    }
+    if (g.smoothstep) {
+      q.w[d] = t * t * (3.f - 2.f * t);
+      q.dw[d] = 6.f * t * (1.f - t) * s;
+      q.d2w[d] = (6.f - 12.f * t) * s * s;
+    } else {
+      q.w[d] = t;
+      q.dw[d] = s;
+      q.d2w[d] = 0.f;
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t corner_row(const sdfb200_grid_t& g, int l, uint32_t ix, uint32_t iy, uint32_t iz) {
+  if (g.layout == SDFB200_GRID_TORCH) {
+    const uint32_t mask = (1u << g.log2_hashmap_size) - 1u;
+    return g.offset[l] + ((ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) & mask);
+  }
+  const uint32_t res = g.resolution[l];
+  uint32_t idx = g.hashed[l] ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
+  return g.offset[l] + idx % g.size[l];
+}
+
 }  // namespace sdfb200

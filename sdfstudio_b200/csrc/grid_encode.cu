@@ -106,6 +106,77 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__
   }
 }
 
+// second-order backward (the backward of k_grid_encode_bwd's dx01 output), needed by the eikonal loss
+// (models/base_surface_model.py:358-362 differentiates |grad sdf| w.r.t. the parameters):
+//   first backward:  dx[c] = sum_lf dout[lf] * J[lf][c](x, table)
+//   given g_dx = dLoss/d(dx):  g_dout[lf] = sum_c g_dx[c] J[lf][c];   g_table[corner][f] += dout[lf] * sum_c g_dx[c] dW_corner/dx_c;
+//                              g_x[c'] += sum_lf dout[lf] sum_c g_dx[c] d2 feat_lf / dx_c dx_c'
+template <typename T, int F>
+__global__ void __launch_bounds__(256) k_grid_encode_bwd2(const __grid_constant__ sdfb200_grid_t g, const void* __restrict__ table,
+                                                          const float* __restrict__ x01, const float* __restrict__ dout,
+                                                          const float* __restrict__ g_dx, int64_t n, float* __restrict__ g_dout,
+                                                          float* __restrict__ g_table, float* __restrict__ g_x) {
+  const int L = g.n_levels;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * L) return;
+  const int64_t p = idx / L;
+  const int l = (int)(idx - p * L);
+  float* gdo = g_dout ? g_dout + p * L * F + l * F : nullptr;
+  if (l >= g.active_levels) {
+    if (gdo)
+#pragma unroll
+      for (int f = 0; f < F; ++f) gdo[f] = 0.f;
+    return;
+  }
+  const float x[3] = {__ldg(x01 + p * 3), __ldg(x01 + p * 3 + 1), __ldg(x01 + p * 3 + 2)};
+  const float gx[3] = {__ldg(g_dx + p * 3), __ldg(g_dx + p * 3 + 1), __ldg(g_dx + p * 3 + 2)};
+  float go[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) go[f] = __ldg(dout + p * L * F + l * F + f);
+  LevelGeom q;
+  level_geom(g, l, x, q);
+  float acc_do[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc_do[f] = 0.f;
+  float acc_x[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const int b[3] = {c & 1, (c >> 1) & 1, (c >> 2) & 1};
+    float A[3], sg[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      A[d] = b[d] ? q.w[d] : 1.f - q.w[d];
+      sg[d] = b[d] ? 1.f : -1.f;
+    }
+    const uint64_t row = corner_row(g, l, q.c[0][b[0]], q.c[1][b[1]], q.c[2][b[2]]);
+    float v[F];
+    TableLoad<T, F>::load(table, row, v);
+    // first derivatives of the corner weight
+    const float d0 = sg[0] * q.dw[0], d1 = sg[1] * q.dw[1], d2 = sg[2] * q.dw[2];
+    const float gW = gx[0] * d0 * A[1] * A[2] + gx[1] * A[0] * d1 * A[2] + gx[2] * A[0] * A[1] * d2;
+    float dot = 0.f;
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      acc_do[f] = fmaf(gW, v[f], acc_do[f]);
+      dot = fmaf(go[f], v[f], dot);
+      if (g_table) atomicAdd(g_table + row * F + f, gW * go[f]);
+    }
+    if (g_x) {
+      const float h00 = sg[0] * q.d2w[0] * A[1] * A[2], h11 = A[0] * sg[1] * q.d2w[1] * A[2], h22 = A[0] * A[1] * sg[2] * q.d2w[2];
+      const float h01 = d0 * d1 * A[2], h02 = d0 * A[1] * d2, h12 = A[0] * d1 * d2;
+      acc_x[0] = fmaf(dot, gx[0] * h00 + gx[1] * h01 + gx[2] * h02, acc_x[0]);
+      acc_x[1] = fmaf(dot, gx[0] * h01 + gx[1] * h11 + gx[2] * h12, acc_x[1]);
+      acc_x[2] = fmaf(dot, gx[0] * h02 + gx[1] * h12 + gx[2] * h22, acc_x[2]);
+    }
+  }
+  if (gdo)
+#pragma unroll
+    for (int f = 0; f < F; ++f) gdo[f] = acc_do[f];
+  if (g_x) {
+    atomicAdd(g_x + p * 3 + 0, acc_x[0]); atomicAdd(g_x + p * 3 + 1, acc_x[1]); atomicAdd(g_x + p * 3 + 2, acc_x[2]);
+  }
+}
+
 int validate_grid(const sdfb200_grid_t* g) {
   SDFB_REQUIRE(g != nullptr, "grid descriptor is NULL");
   SDFB_REQUIRE(g->n_levels >= 1 && g->n_levels <= SDFB200_MAX_LEVELS, "grid.n_levels out of range");
@@ -136,6 +207,15 @@ static int launch_encode_bwd(const sdfb200_grid_t& g, const void* table, const f
   const int64_t total = n * g.n_levels;
   k_grid_encode_bwd<T, F><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(g, table, x01, dout, n, dtable, dx01);
   SDFB_LAUNCHED("k_grid_encode_bwd");
+  return 0;
+}
+
+template <typename T, int F>
+static int launch_encode_bwd2(const sdfb200_grid_t& g, const void* table, const float* x01, const float* dout, const float* g_dx, int64_t n,
+                              float* g_dout, float* g_table, float* g_x, cudaStream_t st) {
+  const int64_t total = n * g.n_levels;
+  k_grid_encode_bwd2<T, F><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(g, table, x01, dout, g_dx, n, g_dout, g_table, g_x);
+  SDFB_LAUNCHED("k_grid_encode_bwd2");
   return 0;
 }
 
@@ -179,4 +259,14 @@ extern "C" int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const vo
   if (n == 0) return 0;
   SDFB_REQUIRE(table && x01 && dout && dtable, "NULL pointer");
   SDFB_DISPATCH_GRID(*grid, launch_encode_bwd, *grid, table, x01, dout, n, dtable, dx01, (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_grid_encode_backward_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
+                                                     const float* g_dx01, int64_t n, float* g_dout, float* g_table, float* g_x01, void* stream) {
+  int r = validate_grid(grid);
+  if (r) return r;
+  SDFB_REQUIRE(n >= 0, "n < 0");
+  if (n == 0) return 0;
+  SDFB_REQUIRE(table && x01 && dout && g_dx01, "NULL pointer");
+  SDFB_DISPATCH_GRID(*grid, launch_encode_bwd2, *grid, table, x01, dout, g_dx01, n, g_dout, g_table, g_x01, (cudaStream_t)stream);
 }

@@ -76,7 +76,8 @@ def make_grid_desc(layout: str, n_levels: int, n_features: int, log2_hashmap_siz
 
 
 class _GridEncodeFn(torch.autograd.Function):
-    """out = encode(x; table).  First-order backward to the table (scatter-add) and to x."""
+    """out = encode(x; table).  Differentiable twice: backward is itself an autograd Function (``_GridEncodeBwdFn``) so that
+    ``autograd.grad(sdf, x, create_graph=True)`` (sdf_field.py:655-662) followed by the eikonal loss works like it does over tcnn."""
 
     @staticmethod
     def forward(ctx, x, table, enc):
@@ -91,18 +92,49 @@ class _GridEncodeFn(torch.autograd.Function):
         return out
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, dout):
-        lib = _lib.load()
         x, table = ctx.saved_tensors
-        enc = ctx.enc
+        dx, dtable = _GridEncodeBwdFn.apply(dout, x, table, ctx.enc, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, dtable, None
+
+
+class _GridEncodeBwdFn(torch.autograd.Function):
+    """(dx, dtable) = encode_backward(dout; x, table); its own backward is sdfb200_grid_encode_backward_backward."""
+
+    @staticmethod
+    def forward(ctx, dout, x, table, enc, need_dx, need_dtable):
+        lib = _lib.load()
         dout = _lib.f32c(dout)
         n = x.shape[0]
+        # NOTE: the C entry point always scatters into dtable; it is cheap to allocate and the scatter is skipped for masked levels
         dtable = torch.zeros(table.shape, device=table.device, dtype=torch.float32)
-        dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        dx = torch.zeros_like(x) if need_dx else None
         _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
                                                     _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
-        return dx, dtable.to(table.dtype), None
+        ctx.save_for_backward(dout, x, table)
+        ctx.enc = enc
+        dt = dtable.to(table.dtype) if need_dtable else None
+        if dt is not None:
+            ctx.mark_non_differentiable(dt)
+        return dx, dt
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_dx, g_dtable):
+        if g_dx is None:
+            return None, None, None, None, None, None
+        lib = _lib.load()
+        dout, x, table = ctx.saved_tensors
+        enc = ctx.enc
+        g_dx = _lib.f32c(g_dx)
+        n = x.shape[0]
+        g_dout = torch.empty_like(dout) if ctx.needs_input_grad[0] else None
+        g_x = torch.zeros_like(x) if ctx.needs_input_grad[1] else None
+        g_table = torch.zeros(table.shape, device=table.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        _lib.check(lib.sdfb200_grid_encode_backward_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), _lib.ptr(g_dx), n,
+                                                             _lib.ptr(g_dout), _lib.ptr(g_table), _lib.ptr(g_x), _lib.stream_ptr()),
+                   "sdfb200_grid_encode_backward_backward")
+        return g_dout, g_x, (g_table.to(table.dtype) if g_table is not None else None), None, None, None
 
 
 class Encoding(nn.Module):

@@ -12,6 +12,7 @@ from typing import Callable, Dict, Optional
 import torch
 
 from . import _lib
+from . import autograd_ops as _ag
 
 
 @dataclass
@@ -62,6 +63,9 @@ def rays_of(ray_samples):
 
 def weights_from_alphas(alphas: torch.Tensor, with_transmittance: bool = False):
     """rays.py:194-230.  alphas [R,S,1] -> weights [R,S,1] (, transmittance [R,S+1,1])."""
+    if _ag.needs_grad(alphas):
+        w, T = _ag.WeightsFromAlphasFn.apply(alphas[..., 0])
+        return (w[..., None], T[..., None]) if with_transmittance else w[..., None]
     lib = _lib.load()
     a = _lib.f32c(alphas[..., 0])
     R, S = a.shape
@@ -73,6 +77,9 @@ def weights_from_alphas(alphas: torch.Tensor, with_transmittance: bool = False):
 
 def weights_from_density(bins: torch.Tensor, densities: torch.Tensor, with_transmittance: bool = False):
     """rays.py:146-192.  bins [R,S+1] euclidean, densities [R,S,1]."""
+    if _ag.needs_grad(densities):
+        w, T = _ag.WeightsFromDensityFn.apply(densities[..., 0], bins)
+        return (w[..., None], T[..., None]) if with_transmittance else w[..., None]
     lib = _lib.load()
     d = _lib.f32c(densities[..., 0])
     R, S = d.shape

@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import autograd_ops as _ag
 from .rays import bins_of
 
 
@@ -24,8 +25,47 @@ def _minmax_init(dev):
     return t.clone()
 
 
+def _background(background, R, dev):
+    """-> (bg_mode, bg tensor | None)"""
+    if isinstance(background, str):
+        if background == "last_sample":
+            return _lib.BG_LAST_SAMPLE, None
+        if background == "random":
+            return _lib.BG_PER_RAY, torch.rand(R, 3, device=dev)
+        raise ValueError(f"unknown background {background!r}")
+    bg_t = _lib.f32c(torch.as_tensor(background, dtype=torch.float32).to(dev))
+    return (_lib.BG_PER_RAY if bg_t.dim() == 2 else _lib.BG_COLOR), bg_t
+
+
+def _render_grad(weights, rgb, normals, bins, background, clamp01, depth_method, want_acc, want_normal, clip_depth):
+    """training path of _render: same outputs through RenderFn (explicit backward kernels)."""
+    if depth_method == "median":
+        bins_k, med = None, True
+    else:
+        bins_k, med = (bins if depth_method is not None else None), False
+    R = weights.shape[0]
+    bg_mode, bg_t = _background(background, R, weights.device) if rgb is not None else (_lib.BG_COLOR, None)
+    o_rgb, o_depth, o_nrm, o_acc, mm = _ag.RenderFn.apply(weights[..., 0], rgb, normals if want_normal else None, bins_k, bg_t, bg_mode)
+    res = {}
+    if rgb is not None:
+        res["rgb"] = torch.clamp(o_rgb, 0.0, 1.0) if clamp01 else o_rgb
+    if want_normal:
+        res["normal"] = o_nrm
+    if want_acc:
+        res["accumulation"] = o_acc[:, None]
+    if med:
+        with torch.no_grad():  # median depth is an index pick: no gradient (torch.searchsorted in the reference)
+            res["depth"] = _render(weights.detach(), bins=bins, depth_method="median")["depth"]
+    elif depth_method is not None:
+        d = torch.clamp(o_depth, min=mm[0], max=mm[1]) if clip_depth else o_depth
+        res["depth"] = d[:, None]
+    return res
+
+
 def _render(weights, rgb=None, normals=None, bins=None, background=None, clamp01=False, depth_method: Optional[str] = None,
             want_acc=False, want_normal=False, clip_depth=True):
+    if _ag.needs_grad(weights, rgb, normals if want_normal else None):
+        return _render_grad(weights, rgb, normals, bins, background, clamp01, depth_method, want_acc, want_normal, clip_depth)
     lib = _lib.load()
     w = _lib.f32c(weights[..., 0])
     R, S = w.shape
@@ -137,6 +177,15 @@ def render_all(weights, rgb, normals, ray_samples, background, training: bool = 
 def render_from_alphas(alphas, rgb, normals, ray_samples, background, training: bool = False, want_weights: bool = True):
     """alphas [R,S,1] -> weights + rgb + expected depth + normal + accumulation + bg_transmittance in ONE launch
     (sdfb200_render_alphas): the fused form of get_weights_and_transmittance_from_alphas + the four renderers."""
+    if _ag.needs_grad(alphas, rgb, normals):
+        R = alphas.shape[0]
+        bg_mode, bg_t = _background(background, R, alphas.device)
+        w, o_rgb, o_depth, o_nrm, o_acc, o_bgT, mm = _ag.RenderAlphasFn.apply(alphas[..., 0], rgb, normals, bins_of(ray_samples), bg_t, bg_mode)
+        res = {"rgb": o_rgb if training else torch.clamp(o_rgb, 0.0, 1.0), "depth": torch.clamp(o_depth, min=mm[0], max=mm[1])[:, None],
+               "normal": o_nrm, "accumulation": o_acc[:, None], "bg_transmittance": o_bgT[:, None]}
+        if want_weights:
+            res["weights"] = w[..., None]
+        return res
     lib = _lib.load()
     a = _lib.f32c(alphas[..., 0])
     R, S = a.shape

@@ -15,6 +15,7 @@ import torch
 from torch import nn
 
 from . import _lib
+from . import sdf_field_train as _train
 from .encoding import Encoding, growth_factor
 from .field_heads import FieldHeadNames
 from .rays import bins_of, rays_of
@@ -349,10 +350,6 @@ class SDFField(nn.Module):
     def _run(self, origins, directions, bins, n_samples: int, wants, apply_contraction: bool, appearance=None) -> Dict[str, torch.Tensor]:
         """origins [R,3] (or points [N,3] in point mode), directions [R,3] | None, bins [R,S+1] | None.
         `wants`: iterable of output names of sdfb200_field_out_t.  Returns flat tensors ([N] / [N,k])."""
-        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self._mlp_params()):
-            raise NotImplementedError(
-                "sdfstudio_b200.SDFField: the differentiable (training) path is not available in this build; "
-                "call under torch.no_grad() / .eval() for rendering.")
         lib = _lib.load()
         dev = self.aabb.device
         if dev.type != "cuda":
@@ -383,15 +380,27 @@ class SDFField(nn.Module):
                    "sdfb200_field_forward")
         return outs
 
+    def _differentiable(self) -> bool:
+        """True when autograd is recording a training step: the methods below then return graph-carrying tensors from the
+        autograd composition in sdf_field_train.py (grid operator = this package's kernels incl. double backward).  Everything
+        under torch.no_grad() -- samplers, evaluation, meshing -- and eval mode runs the fused kernels."""
+        return torch.is_grad_enabled() and self.training and (self.encoding.table.requires_grad or any(p.requires_grad for p in self._mlp_params()))
+
     # ------------------------------------------------------------------ reference methods
     def forward_geonetwork(self, inputs):
         """sdf_field.py:380-410: [N,3] -> [N, 1+geo_feat_dim]."""
+        if self._differentiable():
+            return _train.forward_geonetwork(self, inputs)
         pts = _lib.f32c(inputs.reshape(-1, 3))
         o = self._run(pts, None, None, 1, ("sdf", "geo_feature"), apply_contraction=False)
         return torch.cat([o["sdf"][:, None], o["geo_feature"]], dim=-1)
 
     def get_sdf(self, ray_samples):
         """sdf_field.py:412-418 (NOTE: un-contracted start positions, like the reference)."""
+        if self._differentiable():
+            pos = ray_samples.frustums.get_start_positions()
+            h = _train.forward_geonetwork(self, pos.reshape(-1, 3)).view(*ray_samples.frustums.shape, -1)
+            return h[..., :1]
         origins, directions = rays_of(ray_samples)
         bins = bins_of(ray_samples)
         S = bins.shape[1] - 1
@@ -400,6 +409,8 @@ class SDFField(nn.Module):
 
     def gradient(self, x, skip_spatial_distortion=False, return_sdf=False):
         """sdf_field.py:424-465."""
+        if self._differentiable():
+            return _train.gradient(self, x, skip_spatial_distortion, return_sdf)
         pts = _lib.f32c(x.reshape(-1, 3))
         wants = ["gradients"] + (["sampled_sdf"] if return_sdf and self.config.use_numerical_gradients else [])
         o = self._run(pts, None, None, 1, wants, apply_contraction=not skip_spatial_distortion)
@@ -411,6 +422,10 @@ class SDFField(nn.Module):
 
     def get_density(self, ray_samples):
         """sdf_field.py:467-474."""
+        if self._differentiable():
+            pos = ray_samples.frustums.get_start_positions()
+            h = _train.forward_geonetwork(self, pos.reshape(-1, 3)).view(*ray_samples.frustums.shape, -1)
+            return self.laplace_density(h[..., :1]), h[..., 1:]
         origins, directions = rays_of(ray_samples)
         bins = bins_of(ray_samples)
         S = bins.shape[1] - 1
@@ -423,6 +438,16 @@ class SDFField(nn.Module):
         origins, directions = rays_of(ray_samples)
         bins = bins_of(ray_samples)
         R, S = origins.shape[0], bins.shape[1] - 1
+        if self._differentiable():
+            if sdf is None or gradients is None:
+                inputs = ray_samples.frustums.get_start_positions().reshape(-1, 3)
+                inputs.requires_grad_(True)
+                with torch.enable_grad():
+                    sdf = _train.forward_geonetwork(self, inputs)[:, :1]
+                gradients = torch.autograd.grad(sdf, inputs, torch.ones_like(sdf), create_graph=True, retain_graph=True, only_inputs=True)[0]
+                sdf = sdf.view(*ray_samples.frustums.shape, -1)
+                gradients = gradients.view(*ray_samples.frustums.shape, -1)
+            return _train.get_alpha(self, ray_samples, sdf, gradients)
         if sdf is None or gradients is None:
             o = self._run(origins, directions, bins, S, ("alpha",), apply_contraction=False)
             return o["alpha"].view(R, S, 1)
@@ -451,6 +476,8 @@ class SDFField(nn.Module):
         """sdf_field.py:614-689."""
         if ray_samples.camera_indices is None:
             raise AttributeError("Camera indices are not provided.")
+        if self._differentiable():
+            return _train.get_outputs(self, ray_samples, return_alphas=return_alphas, return_occupancy=return_occupancy)
         origins, directions = rays_of(ray_samples)
         bins = bins_of(ray_samples)
         R, S = origins.shape[0], bins.shape[1] - 1

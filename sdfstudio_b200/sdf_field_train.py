@@ -1,0 +1,176 @@
+"""Differentiable (training) path of SDFField.
+
+What trains in the reference is ATen autograd over ``nn.Linear`` layers plus the ``tinycudann.Encoding`` operator
+(nerfstudio/fields/sdf_field.py:380-410, :614-689).  This module is that composition with the grid operator replaced by this
+package's kernels -- forward, backward and the second-order backward the eikonal term needs
+(sdfb200_grid_encode / _backward / _backward_backward) -- and the dense layers left to ATen exactly like the reference.
+The fused tcgen05 kernel (csrc/field_tc.cu) is the rendering / sampling path (everything under ``torch.no_grad``: the NeuS /
+error-bounded / UniSurf samplers, evaluation, mesh extraction); a fused training kernel is future work.
+
+Functions take the SDFField module as first argument; SDFField dispatches here when autograd is recording in training mode.
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from .field_heads import FieldHeadNames
+
+# 21 icosahedron directions of the off-axis encoding (field_components/encodings.py:129-153), [3, 21]
+_OFF_AXIS = [
+    [0.8506508, 0, 0.5257311], [0.809017, 0.5, 0.309017], [0.5257311, 0.8506508, 0], [1, 0, 0], [0.809017, 0.5, -0.309017],
+    [0.8506508, 0, -0.5257311], [0.309017, 0.809017, -0.5], [0, 0.5257311, -0.8506508], [0.5, 0.309017, -0.809017], [0, 1, 0],
+    [-0.5257311, 0.8506508, 0], [-0.309017, 0.809017, -0.5], [0, 0.5257311, 0.8506508], [-0.309017, 0.809017, 0.5],
+    [0.309017, 0.809017, 0.5], [0.5, 0.309017, 0.809017], [0.5, -0.309017, 0.809017], [0, 0, 1], [-0.5, 0.309017, 0.809017],
+    [-0.809017, 0.5, 0.309017], [-0.809017, 0.5, -0.309017],
+]  # fmt: skip
+
+
+def nerf_encoding(x, num_frequencies: int, max_exp: float, include_input: bool, off_axis: bool = False):
+    """NeRFEncoding.forward (encodings.py:167-208), min_freq_exp = 0."""
+    freqs = 2 ** torch.linspace(0.0, max_exp, num_frequencies, device=x.device)
+    base = x @ torch.tensor(_OFF_AXIS, device=x.device, dtype=x.dtype).T if off_axis else x
+    scaled = (base[..., None] * freqs).reshape(*base.shape[:-1], -1)
+    enc = torch.sin(torch.cat([scaled, scaled + torch.pi / 2.0], dim=-1))
+    return torch.cat([enc, x], dim=-1) if include_input else enc
+
+
+def forward_geonetwork(field, inputs):
+    """sdf_field.py:380-410."""
+    c = field.config
+    if field.use_grid_feature:
+        positions = (inputs + 2.0) / 4.0
+        feature = field.encoding(positions)
+        feature = feature * field.hash_encoding_mask.to(feature.device)
+    else:
+        feature = torch.zeros_like(inputs[:, :1].repeat(1, field.encoding.n_output_dims))
+    pe = nerf_encoding(inputs, c.position_encoding_max_degree, c.position_encoding_max_degree - 1, False, c.off_axis)
+    if not c.use_position_encoding:
+        pe = torch.zeros_like(pe)
+    inputs = torch.cat((inputs, pe, feature), dim=-1)
+    x = inputs
+    for l in range(0, field.num_layers - 1):
+        lin = getattr(field, "glin" + str(l))
+        if l in field.skip_in:
+            x = torch.cat([x, inputs], 1) / np.sqrt(2)
+        x = lin(x)
+        if l < field.num_layers - 2:
+            x = F.softplus(x, beta=100)
+    return x
+
+
+def gradient(field, x, skip_spatial_distortion=False, return_sdf=False):
+    """sdf_field.py:424-465."""
+    if field.spatial_distortion is not None and not skip_spatial_distortion:
+        x = field.spatial_distortion(x)
+    points_sdf = None
+    if field.config.use_numerical_gradients:
+        delta = field.numerical_gradients_delta
+        offs = torch.tensor([[delta, 0, 0], [-delta, 0, 0], [0, delta, 0], [0, -delta, 0], [0, 0, delta], [0, 0, -delta]], device=x.device, dtype=x.dtype)
+        points = x[None] + offs.view(6, *([1] * (x.dim() - 1)), 3)
+        points_sdf = forward_geonetwork(field, points.view(-1, 3))[..., 0].view(6, *x.shape[:-1])
+        gradients = torch.stack([0.5 * (points_sdf[0] - points_sdf[1]) / delta, 0.5 * (points_sdf[2] - points_sdf[3]) / delta,
+                                 0.5 * (points_sdf[4] - points_sdf[5]) / delta], dim=-1)
+    else:
+        with torch.enable_grad():
+            if not x.requires_grad:
+                x.requires_grad_(True)
+            y = forward_geonetwork(field, x)[:, :1]
+            gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True, only_inputs=True)[0]
+    return (gradients, points_sdf) if return_sdf else gradients
+
+
+def get_colors(field, points, directions, gradients, geo_features, camera_indices):
+    """sdf_field.py:532-612."""
+    c = field.config
+    gf = geo_features.view(-1, c.geo_feat_dim)
+    if c.use_diffuse_color:
+        raw_rgb_diffuse = field.diffuse_color_pred(gf)
+    if c.use_specular_tint:
+        tint = torch.sigmoid(field.specular_tint_pred(gf))
+    normals = F.normalize(gradients, p=2, dim=-1)
+    if c.use_reflections:
+        refdirs = 2.0 * torch.sum(normals * -directions, dim=-1, keepdim=True) * normals + directions
+        d = nerf_encoding(refdirs, 4, 3.0, True)
+    else:
+        d = nerf_encoding(directions, 4, 3.0, True)
+    if field.training:
+        emb = field.embedding_appearance(camera_indices)
+        if not c.use_appearance_embedding:
+            emb = torch.zeros_like(emb)
+    elif field.use_average_appearance_embedding:
+        emb = torch.ones((*directions.shape[:-1], c.appearance_embedding_dim), device=directions.device) * field.embedding_appearance.mean(dim=0)
+    else:
+        emb = torch.zeros((*directions.shape[:-1], c.appearance_embedding_dim), device=directions.device)
+    emb = emb.view(-1, c.appearance_embedding_dim)
+    h = [d, gf, emb] if c.use_diffuse_color else [points, d, gradients, gf, emb]
+    if c.use_n_dot_v:
+        h.append(torch.sum(normals * directions, dim=-1, keepdim=True))
+    h = torch.cat(h, dim=-1)
+    for l in range(0, field.num_layers_color - 1):
+        h = getattr(field, "clin" + str(l))(h)
+        if l < field.num_layers_color - 2:
+            h = torch.relu(h)
+    rgb = torch.sigmoid(h)
+    if c.use_diffuse_color:
+        diffuse_linear = torch.sigmoid(raw_rgb_diffuse - math.log(3.0))
+        specular_linear = tint * rgb if c.use_specular_tint else 0.5 * rgb
+        rgb = torch.clamp(specular_linear + diffuse_linear, 0.0, 1.0)
+    return rgb * (1 + 2 * c.rgb_padding) - c.rgb_padding
+
+
+def get_alpha(field, ray_samples, sdf, gradients):
+    """sdf_field.py:476-525."""
+    inv_s = field.deviation_network.get_variance()
+    true_cos = (ray_samples.frustums.directions * gradients).sum(-1, keepdim=True)
+    r = field._cos_anneal_ratio
+    iter_cos = -(F.relu(-true_cos * 0.5 + 0.5) * (1.0 - r) + F.relu(-true_cos) * r)
+    deltas = ray_samples.deltas
+    prev_cdf = torch.sigmoid((sdf - iter_cos * deltas * 0.5) * inv_s)
+    next_cdf = torch.sigmoid((sdf + iter_cos * deltas * 0.5) * inv_s)
+    return ((prev_cdf - next_cdf + 1e-5) / (prev_cdf + 1e-5)).clip(0.0, 1.0)
+
+
+def get_outputs(field, ray_samples, return_alphas=False, return_occupancy=False):
+    """sdf_field.py:614-689."""
+    if ray_samples.camera_indices is None:
+        raise AttributeError("Camera indices are not provided.")
+    c = field.config
+    shape = ray_samples.frustums.directions.shape[:-1]
+    camera_indices = ray_samples.camera_indices.squeeze()
+    inputs = ray_samples.frustums.get_start_positions().reshape(-1, 3)
+    directions_flat = ray_samples.frustums.directions.reshape(-1, 3)
+    if field.spatial_distortion is not None:
+        inputs = field.spatial_distortion(inputs)
+    points_norm = inputs.norm(dim=-1)
+    if not inputs.requires_grad:
+        inputs.requires_grad_(True)
+    with torch.enable_grad():
+        h = forward_geonetwork(field, inputs)
+        sdf, geo_feature = torch.split(h, [1, c.geo_feat_dim], dim=-1)
+    if c.use_numerical_gradients:
+        gradients, sampled_sdf = gradient(field, inputs, skip_spatial_distortion=True, return_sdf=True)
+        sampled_sdf = sampled_sdf.view(-1, *shape).permute(1, 2, 0).contiguous()
+    else:
+        gradients = torch.autograd.grad(outputs=sdf, inputs=inputs, grad_outputs=torch.ones_like(sdf), create_graph=True, retain_graph=True,
+                                        only_inputs=True)[0]
+        sampled_sdf = None
+    rgb = get_colors(field, inputs, directions_flat, gradients, geo_feature, camera_indices)
+    density = field.laplace_density(sdf)
+    rgb, sdf, density = rgb.view(*shape, -1), sdf.view(*shape, -1), density.view(*shape, -1)
+    gradients = gradients.view(*shape, -1)
+    outputs = {
+        FieldHeadNames.RGB: rgb,
+        FieldHeadNames.DENSITY: density,
+        FieldHeadNames.SDF: sdf,
+        FieldHeadNames.NORMAL: F.normalize(gradients, p=2, dim=-1),
+        FieldHeadNames.GRADIENT: gradients,
+        "points_norm": points_norm.view(*shape, -1),
+        "sampled_sdf": sampled_sdf,
+    }
+    if return_alphas:
+        outputs[FieldHeadNames.ALPHA] = get_alpha(field, ray_samples, sdf, gradients)
+    if return_occupancy:
+        outputs[FieldHeadNames.OCCUPANCY] = field.get_occupancy(sdf)
+    return outputs
