@@ -15,9 +15,10 @@ from sdfstudio_b200.synthetic import dtu_like_rays  # noqa: E402
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 dev = torch.device("cuda")
 log2t = int(sys.argv[2]) if len(sys.argv) > 2 else 19
+tdt = sys.argv[3] if len(sys.argv) > 3 else "fp32"
 torch.manual_seed(0)
 cfg = sb.SDFFieldConfig(use_grid_feature=True, num_layers=2, num_layers_color=2, hidden_dim=256, bias=0.5, beta_init=0.3, inside_outside=False,
-                        log2_hashmap_size=log2t, grid_layout="torch", precision=prec)
+                        log2_hashmap_size=log2t, grid_layout="torch", precision=prec, table_dtype=tdt)
 from sdfstudio_b200.synthetic import perturb_field_  # noqa: E402
 field = perturb_field_(sb.SDFField(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=49), 0).to(dev).eval()
 o, d, cam, nears, fars = dtu_like_rays(4096, 1000)
