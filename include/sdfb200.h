@@ -264,6 +264,34 @@ int sdfb200_render_alphas(const float* alphas, const float* rgb, const float* no
 /* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
 int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * The step before the path: camera rays, colliders, meshing lattice.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define SDFB200_CAMERA_PERSPECTIVE 1 /* CameraType.PERSPECTIVE.value, cameras/cameras.py:38-43 */
+#define SDFB200_CAMERA_FISHEYE 2
+#define SDFB200_COLLIDER_AABB 0
+#define SDFB200_COLLIDER_NEAR_FAR 1
+#define SDFB200_COLLIDER_SPHERE 2
+
+/* Cameras._generate_rays_from_coords (cameras/cameras.py:459-695) for perspective / fisheye cameras without distortion
+ * parameters.  Per-camera arrays fx, fy, cx, cy [C], camera_type [C] (NULL = all perspective), camera_to_worlds [C,3,4];
+ * per-ray camera_indices [N] (int32) and coords [N,2] = (y, x) pixel coordinates (already offset by 0.5 by the caller, like
+ * the reference).  Outputs: origins, directions [N,3]; pixel_area, directions_norm [N] (may be NULL). */
+int sdfb200_generate_rays(const float* fx, const float* fy, const float* cx, const float* cy, const int32_t* camera_type,
+                          const float* camera_to_worlds, int32_t n_cameras, const int32_t* camera_indices, const float* coords,
+                          int64_t n_rays, float* origins, float* directions, float* pixel_area, float* directions_norm, void* stream);
+
+/* scene_colliders.py:47-163.  `params` is a HOST array: AABB = {min x,y,z, max x,y,z} (:56-98, near_plane clamp :92-94),
+ * NEAR_FAR = {near, far} (:116-134), SPHERE = {radius, soft_intersection != 0, radius**2} (:137-163).  nears / fars [N]. */
+int sdfb200_collide(const float* origins, const float* directions, int64_t n_rays, int32_t collider_type, const float* params,
+                    float near_plane, float* nears, float* fars, void* stream);
+
+/* points [n,3] = entries [start, start+n) of np.meshgrid(np.linspace(min, max, res) x3, indexing="ij") flattened
+ * (utils/marching_cubes.py:49-56): the lattice is generated on the device chunk by chunk instead of being materialised.
+ * bbox_min / bbox_max (double[3]) and resolution (int32[3]) are HOST arrays. */
+int sdfb200_lattice_points(const double* bbox_min, const double* bbox_max, const int32_t* resolution, int64_t start, int64_t n,
+                           float* points, void* stream);
+
 /* Training path: backward of sdfb200_render (expected depth) / sdfb200_render_alphas' compositing w.r.t. the per-sample
  * inputs (autograd over renderers.py:42-295 in the reference).  `accumulation`, `depth` = forward outputs (depth BEFORE the
  * global clip).  g_rgb [R,3], g_depth [R], g_normal [R,3], g_accumulation [R], g_weights_in [R,S]: incoming gradients, each

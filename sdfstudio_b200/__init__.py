@@ -9,6 +9,7 @@ Host side mirrors the reference's plug points:
 All arithmetic runs in libsdfb200.so (CUDA, sm_100a) behind the C ABI of include/sdfb200.h.  No CPU / PyTorch fallback.
 """
 from . import _lib  # noqa: F401
+from . import cameras, meshing  # noqa: F401
 from .density_fields import HashMLPDensityField  # noqa: F401
 from .encoding import Encoding, HashEncoding  # noqa: F401
 from .field_heads import FieldHeadNames  # noqa: F401
@@ -18,6 +19,7 @@ from .ray_samplers import (  # noqa: F401
     SqrtSampler, UniformLinDispPiecewiseSampler, UniformSampler, UniSurfSampler,
 )
 from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, SemanticRenderer, render_all, render_from_alphas  # noqa: F401
+from .scene_colliders import AABBBoxCollider, NearFarCollider, SceneCollider, SphereCollider  # noqa: F401
 from .spatial_distortions import SceneContraction  # noqa: F401
 from .sdf_field import LaplaceDensity, SDFField, SDFFieldConfig, SingleVarianceNetwork  # noqa: F401
 

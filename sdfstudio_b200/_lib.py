@@ -19,6 +19,8 @@ DT_F32, DT_F16 = 0, 1
 CONTRACT_NONE, CONTRACT_LINF, CONTRACT_L2 = 0, 1, 2
 SPACING = {"uniform": 0, "lindisp": 1, "sqrt": 2, "log": 3, "piecewise": 4, "identity": 5}
 BG_COLOR, BG_LAST_SAMPLE, BG_PER_RAY = 0, 1, 2
+CAMERA_PERSPECTIVE, CAMERA_FISHEYE = 1, 2
+COLLIDER_AABB, COLLIDER_NEAR_FAR, COLLIDER_SPHERE = 0, 1, 2
 PRECISION = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
 
@@ -81,6 +83,9 @@ _PROTOS = {
     "sdfb200_grid_encode_backward_backward": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sdfb200_render_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdfb200_weights_backward": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "sdfb200_generate_rays": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "sdfb200_collide": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_float), _f32, _vp, _vp, _vp]),
+    "sdfb200_lattice_points": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), _i64, _i64, _vp, _vp]),
     "sdfb200_field_packed_bytes": (_sz, [C.POINTER(FieldDesc)]),
     "sdfb200_field_pack": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), _vp, _vp]),
     "sdfb200_field_workspace_bytes": (_sz, [C.POINTER(FieldDesc), _i64]),

@@ -102,3 +102,30 @@ def test_field_driven_samplers(golden_dir, name):
     close(ub.euclid, G["uni_euclid"], rtol=0, atol=4e-6)
     if mask.any():
         close(surf, G["uni_surface"], rtol=1e-5, atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# step before the path: camera rays, colliders, meshing lattice
+# ---------------------------------------------------------------------------------------------------------------
+def test_raygen_oracle_matches_reference_golden(golden_dir):
+    from oracle import raygen
+
+    g = load(golden_dir, "raygen")
+    c = raygen.raygen_case()
+    o, d, area, dnorm = raygen.generate_rays(c["fx"], c["fy"], c["cx"], c["cy"], c["cam_type"], c["c2w"], c["idx"], c["coords"])
+    assert torch.equal(o, g["origins"])
+    assert torch.equal(d, g["directions"])
+    assert torch.equal(dnorm, g["directions_norm"])
+    assert torch.equal(area, g["pixel_area"])
+    aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])
+    n, f = raygen.collide_aabb(o, d, aabb, near_plane=0.05)
+    assert torch.equal(n, g["aabb_train_nears"]) and torch.equal(f, g["aabb_train_fars"])
+    n, f = raygen.collide_aabb(o, d, aabb, near_plane=0.0)
+    assert torch.equal(n, g["aabb_eval_nears"]) and torch.equal(f, g["aabb_eval_fars"])
+    n, f = raygen.collide_near_far(o, 0.5, 4.5)
+    assert torch.equal(n, g["nf_nears"]) and torch.equal(f, g["nf_fars"])
+    n, f = raygen.collide_sphere(o, d, 1.3, False)
+    assert torch.equal(n, g["sph_nears"]) and torch.equal(f, g["sph_fars"])
+    n, f = raygen.collide_sphere(o, d, 1.3, True)
+    assert torch.equal(n, g["sphsoft_nears"]) and torch.equal(f, g["sphsoft_fars"])
+    assert torch.equal(raygen.lattice((-1.0, -0.7, -1.0), (0.3, 1.0, 1.0), (9, 5, 7)), g["lattice"])
