@@ -20,6 +20,7 @@ from .ray_samplers import (  # noqa: F401
 )
 from .renderers import AccumulationRenderer, DepthRenderer, RGBRenderer, SemanticRenderer, render_all, render_from_alphas  # noqa: F401
 from .scene_colliders import AABBBoxCollider, NearFarCollider, SceneCollider, SphereCollider  # noqa: F401
+from .surface_model import SurfaceRenderer  # noqa: F401
 from .spatial_distortions import SceneContraction  # noqa: F401
 from .sdf_field import LaplaceDensity, SDFField, SDFFieldConfig, SingleVarianceNetwork  # noqa: F401
 

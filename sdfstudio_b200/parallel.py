@@ -20,8 +20,12 @@ def shard_bounds(n_rays: int, rank: int, world_size: int) -> Tuple[int, int]:
 
 def shard_ray_bundle(ray_bundle, rank: int, world_size: int):
     """Slice every per-ray tensor field of a (reference or local) RayBundle."""
-    n = ray_bundle.origins.shape[0]
-    s, e = shard_bounds(n, rank, world_size)
+    s, e = shard_bounds(ray_bundle.origins.shape[0], rank, world_size)
+    return slice_ray_bundle(ray_bundle, s, e)
+
+
+def slice_ray_bundle(ray_bundle, s: int, e: int):
+    """rays [s, e) of a flat RayBundle (RayBundle.get_row_major_sliced_ray_bundle, cameras/rays.py:277-293)."""
     kw = {}
     for name in ("origins", "directions", "pixel_area", "directions_norm", "camera_indices", "nears", "fars", "times"):
         v = getattr(ray_bundle, name, None)

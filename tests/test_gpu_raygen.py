@@ -97,3 +97,47 @@ def test_lattice_and_sdf_grid():
     spec, kw, o, d, cam, nears, fars, oracle, field_tc = build_case("neusfacto_c1", precision="bf16x3")
     grid_tc = sb.meshing.evaluate_sdf_grid(field_tc, res, chunk=4096)
     assert float((grid_tc.cpu() - ref).abs().max()) < 5e-5
+
+
+def test_surface_renderer_image_vs_oracle():
+    """cameras -> AABB collider -> NeuS sampler -> SDFField -> renderers as ONE composition (SurfaceRenderer) against the CPU
+    oracle chained the same way; chunked rendering (base_model.py:165-189) reproduces the unchunked image."""
+    import sdfstudio_b200 as sb
+    from oracle import render, samplers
+
+    spec, kw, o_, d_, cam_, nears_, fars_, oracle, field = build_case("neusfacto_c1")
+    c = raygen.raygen_case()
+    H, W = 12, 16
+    persp = torch.full_like(c["cam_type"], raygen.PERSPECTIVE)
+    cams = sb.cameras.Cameras(c["c2w"], c["fx"] / 24, c["fy"] / 24, c["cx"] / 24, c["cy"] / 24, W, H, camera_type=persp, device=torch.device("cuda"))
+    rb = cams.generate_rays(1)
+
+    class _Box:
+        aabb = torch.tensor([[-1.0, -1.0, -1.0], [1.0, 1.0, 1.0]])
+
+    sampler = sb.NeuSSampler(num_samples=16, num_samples_importance=16, num_samples_outside=0, num_upsample_steps=2, base_variance=64).eval()
+    model = sb.SurfaceRenderer(field, sampler, collider=sb.AABBBoxCollider(_Box()).eval(), kind="neus", background_color="white").eval()
+    with torch.no_grad():
+        img = model.get_outputs_for_camera_ray_bundle(rb, image_shape=(H, W))
+        model.eval_num_rays_per_chunk = 50
+        rb2 = cams.generate_rays(1)
+        img_chunked = model.get_outputs_for_camera_ray_bundle(rb2, image_shape=(H, W))
+    assert img["rgb"].shape == (H, W, 3) and img["depth"].shape == (H, W, 1)
+    for k in ("rgb", "normal", "accumulation"):
+        assert torch.equal(img[k], img_chunked[k]), k
+
+    # oracle chain on the same rays
+    ys, xs = torch.meshgrid(torch.arange(float(H)) + 0.5, torch.arange(float(W)) + 0.5, indexing="ij")
+    o, d, area, dn = raygen.generate_rays(c["fx"] / 24, c["fy"] / 24, c["cx"] / 24, c["cy"] / 24, persp, c["c2w"], torch.full((H * W,), 1),
+                                          torch.stack([ys, xs], -1).reshape(-1, 2))
+    o, d = o.contiguous(), d.contiguous()
+    nears, fars = raygen.collide_aabb(o, d, _Box.aabb, 0.0)
+    bins = samplers.neus_sampler(nears, fars, lambda st: oracle.get_sdf(o, d, st), num_samples=16, num_samples_importance=16, num_upsample_steps=2,
+                                 base_variance=64.0)
+    oo = oracle.get_outputs(o, d, bins.starts, bins.deltas, torch.full((H * W,), 1), return_alphas=True)
+    ow, _ = samplers.weights_from_alphas(oo["alphas"][..., 0])
+    orgb = render.render_rgb(oo["rgb"], ow[..., None], torch.ones(3))
+    odepth = render.render_depth(ow[..., None], bins.starts[..., None], bins.ends[..., None], "expected") / dn
+    assert rel_err(img["rgb"].view(-1, 3), orgb, floor=1e-2) < 2e-4
+    assert rel_err(img["depth"].view(-1, 1), odepth, floor=1e-2) < 2e-4
+    assert rel_err(img["accumulation"].view(-1, 1), ow.sum(-1, keepdim=True), floor=1e-2) < 2e-4
