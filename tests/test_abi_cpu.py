@@ -4,6 +4,7 @@ import os
 import re
 
 import pytest
+import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -90,3 +91,59 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{fn} imports oracle"
                 assert "oracle/" not in txt and "oracle." not in txt.replace("oracle.make_golden", ""), f"{fn} references oracle"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# checkpoint compatibility: same state_dict names and shapes as the unmodified reference SDFField
+# (fixture minted by oracle/make_golden_statedict.py), and the trainer's checkpoint layout loads
+# ---------------------------------------------------------------------------------------------------------------
+def _product_field_cpu(name, layout="tcnn"):
+    import json
+
+    import sdfstudio_b200 as sb
+    from oracle import cases
+
+    spec, kw = cases.CASES[name]
+    cfg = sb.SDFFieldConfig(
+        num_layers=spec.num_layers, hidden_dim=spec.hidden_dim, geo_feat_dim=spec.geo_feat_dim, num_layers_color=spec.num_layers_color,
+        hidden_dim_color=spec.hidden_dim_color, appearance_embedding_dim=spec.appearance_embedding_dim,
+        use_appearance_embedding=spec.use_appearance_embedding, use_grid_feature=spec.use_grid_feature,
+        position_encoding_max_degree=spec.position_encoding_max_degree, use_diffuse_color=spec.use_diffuse_color,
+        use_specular_tint=spec.use_specular_tint, use_reflections=spec.use_reflections, use_n_dot_v=spec.use_n_dot_v, off_axis=spec.off_axis,
+        use_numerical_gradients=spec.use_numerical_gradients, num_levels=spec.num_levels, max_res=spec.max_res, base_res=spec.base_res,
+        log2_hashmap_size=min(spec.log2_hashmap_size, 12), hash_features_per_level=spec.hash_features_per_level, hash_smoothstep=spec.hash_smoothstep,
+        use_position_encoding=spec.use_position_encoding, grid_layout=layout)  # fmt: skip
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sdffield_state_keys.json")) as fh:
+        ref = json.load(fh)[name]
+    return sb.SDFField(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=49), ref
+
+
+@pytest.mark.parametrize("name", ["neusfacto_c1", "angelo_small", "bakedsdf_small", "volsdf_stock"])
+def test_state_dict_names_match_reference(name):
+    field, ref = _product_field_cpu(name)
+    mine = {k: list(v.shape) for k, v in field.state_dict().items() if not k.startswith("encoding.")}
+    assert mine == ref
+    assert [k for k in field.state_dict() if k.startswith("encoding.")] == ["encoding.params"]      # tcnn's single flat vector
+
+
+def test_reference_checkpoint_layout_loads():
+    from sdfstudio_b200 import checkpoint
+
+    src, _ = _product_field_cpu("neusfacto_c1")
+    dst, _ = _product_field_cpu("neusfacto_c1")
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.copy_(torch.randn(p.shape, generator=g))
+    # what engine/trainer.py:276-297 writes for a DDP-wrapped pipeline, with tcnn's fp16 grid parameters
+    pipe = {"module._model.field." + k: (v.half() if k == "encoding.params" else v.clone()) for k, v in src.state_dict().items()}
+    pipe["module._model.proposal_networks.0.mlp_base.params"] = torch.zeros(7)
+    pipe["module.datamanager.train_camera_optimizer.pose_adjustment"] = torch.zeros(3, 6)
+    ckpt = {"step": 1000, "pipeline": pipe, "optimizers": {}, "schedulers": {}, "scalers": {}}
+    missing, unexpected = checkpoint.load_field_checkpoint(dst, ckpt)
+    assert not missing and not unexpected
+    for (k, a), (_, b) in zip(src.state_dict().items(), dst.state_dict().items()):
+        assert torch.equal(a.half().float() if k == "encoding.params" else a, b), k
+    torch_layout, _ = _product_field_cpu("neusfacto_c1", layout="torch")
+    with pytest.raises(ValueError):
+        checkpoint.load_field_checkpoint(torch_layout, ckpt)
