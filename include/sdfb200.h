@@ -76,7 +76,7 @@ int sdfb200_grid_encode(const sdfb200_grid_t* grid, const void* table, const flo
                         int64_t out_ld, float* dout_dx, void* stream);
 
 /* backward of the above w.r.t. the table (atomic scatter-add into dtable, fp32, same row layout as the table) and,
- * optionally, w.r.t. x01 (dx01 [n,3], may be NULL).  dout [n, L*F]. */
+ * optionally, w.r.t. x01 (dx01 [n,3], may be NULL).  dout [n, L*F].  dtable may be NULL when only dx01 is wanted. */
 int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
                                  int64_t n, float* dtable, float* dx01, void* stream);
 

@@ -55,7 +55,9 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__
   for (int f = 0; f < F; ++f) go[f] = __ldg(dout + p * L * F + l * F + f);
   const float s = g.scale[l];
   const uint64_t base = g.offset[l];
-  if (g.layout == SDFB200_GRID_TORCH) {
+  if (dtable == nullptr) {
+    // input gradient only (autograd.grad(sdf, x) of the eikonal / normal path): no scatter
+  } else if (g.layout == SDFB200_GRID_TORCH) {
     const float sx = x * s, sy = y * s, sz = z * s;
     const float fxf = floorf(sx), fyf = floorf(sy), fzf = floorf(sz);
     const uint32_t fc[3][2] = {{(uint32_t)(int)fxf, (uint32_t)(int)ceilf(sx)}, {(uint32_t)(int)fyf, (uint32_t)(int)ceilf(sy)}, {(uint32_t)(int)fzf, (uint32_t)(int)ceilf(sz)}};
@@ -257,7 +259,7 @@ extern "C" int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const vo
   if (r) return r;
   SDFB_REQUIRE(n >= 0, "n < 0");
   if (n == 0) return 0;
-  SDFB_REQUIRE(table && x01 && dout && dtable, "NULL pointer");
+  SDFB_REQUIRE(table && x01 && dout && (dtable || dx01), "NULL pointer");
   SDFB_DISPATCH_GRID(*grid, launch_encode_bwd, *grid, table, x01, dout, n, dtable, dx01, (cudaStream_t)stream);
 }
 

@@ -10,6 +10,7 @@ and for the reference's own ``HashEncoding`` (nerfstudio/field_components/encodi
 
 The arithmetic runs in libsdfb200.so (sdfb200_grid_encode / sdfb200_grid_encode_backward); there is no PyTorch path.
 """
+import contextlib
 import math
 from typing import Optional
 
@@ -94,7 +95,10 @@ class _GridEncodeFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dout):
         x, table = ctx.saved_tensors
-        dx, dtable = _GridEncodeBwdFn.apply(dout, x, table, ctx.enc, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        # inside Encoding.inputs_only_backward() (the autograd.grad(sdf, x) of SDFField) the table gradient is not requested:
+        # skip its atomic scatter -- autograd cannot tell a Python Function which of its input gradients a call needs
+        need_dtable = ctx.needs_input_grad[1] and not ctx.enc._inputs_only
+        dx, dtable = _GridEncodeBwdFn.apply(dout, x, table, ctx.enc, ctx.needs_input_grad[0], need_dtable)
         return dx, dtable, None
 
 
@@ -106,14 +110,17 @@ class _GridEncodeBwdFn(torch.autograd.Function):
         lib = _lib.load()
         dout = _lib.f32c(dout)
         n = x.shape[0]
-        # NOTE: the C entry point always scatters into dtable; it is cheap to allocate and the scatter is skipped for masked levels
-        dtable = torch.zeros(table.shape, device=table.device, dtype=torch.float32)
+        dtable = torch.zeros(table.shape, device=table.device, dtype=torch.float32) if need_dtable else None
         dx = torch.zeros_like(x) if need_dx else None
+        if dtable is None and dx is None:
+            ctx.save_for_backward(dout, x, table)
+            ctx.enc = enc
+            return None, None
         _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
                                                     _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
         ctx.save_for_backward(dout, x, table)
         ctx.enc = enc
-        dt = dtable.to(table.dtype) if need_dtable else None
+        dt = dtable.to(table.dtype) if dtable is not None else None
         if dt is not None:
             ctx.mark_non_differentiable(dt)
         return dx, dt
@@ -148,6 +155,7 @@ class Encoding(nn.Module):
         # "fp16": the kernels gather from a half-precision copy of the (fp32 master) parameters, which is what tiny-cuda-nn
         # itself does (fp16 compute params + fp32 master); the copy is refreshed whenever the parameter changes
         self.table_dtype = table_dtype
+        self._inputs_only = False
         self._half_cache = None
         self._half_key = None
         if n_input_dims != 3:
@@ -201,6 +209,16 @@ class Encoding(nn.Module):
         half = self.table_dtype == "fp16" or self.table.dtype == torch.float16
         self._desc.table_dtype = _lib.DT_F16 if half else _lib.DT_F32
         return self._desc
+
+    @contextlib.contextmanager
+    def inputs_only_backward(self):
+        """Backward passes started inside this context compute d/dx only (no table-gradient scatter).  For
+        ``torch.autograd.grad(sdf, x, create_graph=True)``-style calls whose `inputs` do not include the table."""
+        prev, self._inputs_only = self._inputs_only, True
+        try:
+            yield
+        finally:
+            self._inputs_only = prev
 
     def set_active_levels(self, levels: int):
         """levels >= `levels` output zeros (fused form of SDFField.update_mask, sdf_field.py:376-378)."""

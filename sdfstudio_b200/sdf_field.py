@@ -444,7 +444,8 @@ class SDFField(nn.Module):
                 inputs.requires_grad_(True)
                 with torch.enable_grad():
                     sdf = _train.forward_geonetwork(self, inputs)[:, :1]
-                gradients = torch.autograd.grad(sdf, inputs, torch.ones_like(sdf), create_graph=True, retain_graph=True, only_inputs=True)[0]
+                with self.encoding.inputs_only_backward():
+                    gradients = torch.autograd.grad(sdf, inputs, torch.ones_like(sdf), create_graph=True, retain_graph=True, only_inputs=True)[0]
                 sdf = sdf.view(*ray_samples.frustums.shape, -1)
                 gradients = gradients.view(*ray_samples.frustums.shape, -1)
             return _train.get_alpha(self, ray_samples, sdf, gradients)

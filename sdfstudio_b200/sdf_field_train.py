@@ -77,7 +77,8 @@ def gradient(field, x, skip_spatial_distortion=False, return_sdf=False):
             if not x.requires_grad:
                 x.requires_grad_(True)
             y = forward_geonetwork(field, x)[:, :1]
-            gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True, only_inputs=True)[0]
+            with field.encoding.inputs_only_backward():
+                gradients = torch.autograd.grad(outputs=y, inputs=x, grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True, only_inputs=True)[0]
     return (gradients, points_sdf) if return_sdf else gradients
 
 
@@ -153,8 +154,9 @@ def get_outputs(field, ray_samples, return_alphas=False, return_occupancy=False)
         gradients, sampled_sdf = gradient(field, inputs, skip_spatial_distortion=True, return_sdf=True)
         sampled_sdf = sampled_sdf.view(-1, *shape).permute(1, 2, 0).contiguous()
     else:
-        gradients = torch.autograd.grad(outputs=sdf, inputs=inputs, grad_outputs=torch.ones_like(sdf), create_graph=True, retain_graph=True,
-                                        only_inputs=True)[0]
+        with field.encoding.inputs_only_backward():
+            gradients = torch.autograd.grad(outputs=sdf, inputs=inputs, grad_outputs=torch.ones_like(sdf), create_graph=True, retain_graph=True,
+                                            only_inputs=True)[0]
         sampled_sdf = None
     rgb = get_colors(field, inputs, directions_flat, gradients, geo_feature, camera_indices)
     density = field.laplace_density(sdf)
