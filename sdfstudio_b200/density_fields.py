@@ -18,6 +18,53 @@ from . import _lib
 from .encoding import make_grid_desc
 
 
+class _TruncExp(torch.autograd.Function):
+    """field_components/activations.py:24-38: exp forward, gradient g * exp(clamp(x, -15, 15))."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        return g * torch.exp(x.clamp(-15, 15))
+
+
+class _GridFn(torch.autograd.Function):
+    """hash-grid features of the flat tcnn-style parameter vector (grid table = its tail): forward / backward kernels of the
+    Encoding operator, gradient scattered into the tail of d(params)."""
+
+    @staticmethod
+    def forward(ctx, x01, params, nb):
+        lib = _lib.load()
+        x = _lib.f32c(x01)
+        n = x.shape[0]
+        desc = nb.desc
+        desc.active_levels, desc.table_dtype = desc.n_levels, _lib.DT_F32
+        out = torch.empty(n, nb.in_dim, device=x.device, dtype=torch.float32)
+        table = params.detach()[nb.n_net:]
+        _lib.check(lib.sdfb200_grid_encode(desc, table.data_ptr(), _lib.ptr(x), n, _lib.ptr(out), nb.in_dim, None, _lib.stream_ptr()), "sdfb200_grid_encode")
+        ctx.save_for_backward(x, params)
+        ctx.nb = nb
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout):
+        lib = _lib.load()
+        x, params = ctx.saved_tensors
+        nb = ctx.nb
+        dout = _lib.f32c(dout)
+        dparams = torch.zeros_like(params, dtype=torch.float32)
+        dx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+        table = params.detach()[nb.n_net:]
+        _lib.check(lib.sdfb200_grid_encode_backward(nb.desc, table.data_ptr(), _lib.ptr(x), _lib.ptr(dout), x.shape[0], dparams[nb.n_net:].data_ptr(),
+                                                    _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
+        return dx, dparams, None
+
+
 class _NetworkWithInputEncoding(nn.Module):
     def __init__(self, n_levels, n_features, log2_hashmap_size, base_res, per_level_scale, hidden_dim, n_hidden_layers, seed=1337):
         super().__init__()
@@ -77,7 +124,7 @@ class HashMLPDensityField(nn.Module):
     def density_from_positions(self, positions: torch.Tensor, return_pre_activation: bool = False):
         """positions [..., 3] -> density [..., 1] (fields/base_field.py:48-65 + density_fields.py:98-118)."""
         if torch.is_grad_enabled() and self.training and self.mlp_base.params.requires_grad:
-            raise NotImplementedError("sdfstudio_b200.HashMLPDensityField: the differentiable (training) path is not in this build")
+            return self._density_differentiable(positions, return_pre_activation)
         lib = _lib.load()
         pos = _lib.f32c(positions.reshape(-1, 3))
         n = pos.shape[0]
@@ -95,6 +142,27 @@ class HashMLPDensityField(nn.Module):
                                                      _lib.ptr(pos), n, _lib.ptr(dens), _lib.ptr(pre), _lib.stream_ptr()), "sdfb200_density_field_forward")
         dens = dens.view(*positions.shape[:-1], 1)
         return (dens, pre.view(*positions.shape[:-1], 1)) if return_pre_activation else dens
+
+    def _density_differentiable(self, positions, return_pre_activation=False):
+        """Training path (the interlevel loss trains the proposal networks, models/neus_facto.py): the hash grid through this package's
+        twice-differentiable operator (sdfb200_grid_encode / _backward), the width-16..64 ReLU MLP through ATen, trunc_exp with the
+        reference's clipped backward (field_components/activations.py:24-42)."""
+        nb = self.mlp_base
+        x = positions.reshape(-1, 3)
+        if self.spatial_distortion is not None:
+            x01 = (self.spatial_distortion(x) + 2.0) / 4.0
+        else:
+            x01 = (x - self.aabb[0]) / (self.aabb[1] - self.aabb[0])                  # SceneBox.get_normalized_positions
+        feat = _GridFn.apply(x01, nb.params, nb)
+        w = nb.params[: nb.n_net]
+        o = nb.hidden_dim * nb.in_pad
+        h = torch.relu(feat @ w[:o].view(nb.hidden_dim, nb.in_pad)[:, : nb.in_dim].t())
+        for _ in range(nb.n_hidden_layers - 1):
+            h = torch.relu(h @ w[o: o + nb.hidden_dim * nb.hidden_dim].view(nb.hidden_dim, nb.hidden_dim).t())
+            o += nb.hidden_dim * nb.hidden_dim
+        pre = (h @ w[o: o + nb.hidden_dim]).view(*positions.shape[:-1], 1)
+        dens = _TruncExp.apply(pre)
+        return (dens, pre) if return_pre_activation else dens
 
     def density_fn(self, positions: torch.Tensor) -> torch.Tensor:
         return self.density_from_positions(positions)
