@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdfb200.so")
-SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "tc_test.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
+SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "tc_test.cu", "tc_linear.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-Xptxas", "-v"]

@@ -98,6 +98,7 @@ inline int make_field_plan(const sdfb200_field_t& f, FieldPlan& p) {
 // ---- per-chunk workspace (floats), generic fp32 path ----
 struct FieldWorkspace {
   size_t x, x01, in, jac, h[SDFB200_MAX_LAYERS], outg, g0, g1, gin, cin, c0, c1, sdf, grad, nsdf;
+  size_t tcw;            // packed weight planes of one tensor-core GEMM chunk (fixed size, csrc/tc_linear.h)
   size_t floats_per_chunk;
 };
 
@@ -130,6 +131,8 @@ inline void make_workspace_plan(const sdfb200_field_t& f, const FieldPlan& p, in
   w.sdf = take(1);
   w.grad = take(3);
   w.nsdf = take(6);
+  w.tcw = off;
+  off = align_up(off + 65536, 64);   // kTcGemmScratchBytes / 4
   w.floats_per_chunk = off;
 }
 

@@ -9,6 +9,7 @@
 //   k_color_inputs / k_field_post   get_colors :532-612, LaplaceDensity :57-66, get_alpha :476-525
 #include "field_plan.h"
 #include "grid.cuh"
+#include "tc_linear.h"
 
 namespace sdfb200 {
 
@@ -213,8 +214,14 @@ __global__ void __launch_bounds__(256) k_sgemm(const float* __restrict__ X, int 
   }
 }
 
+// GEMM engine of the current field call: 0 planes = the exact-fp32 CUDA-core kernel below; 1 / 2 = the generic tcgen05 Linear
+// (bf16 / bf16x3, csrc/tc_linear.cu) with `scratch` for its packed weight chunk.  Set by field_forward_fp32 for the duration of a call.
+struct GemmEngine { int planes; void* scratch; };
+static thread_local GemmEngine g_gemm = {0, nullptr};
+
 static int sgemm(int epi, const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M, int Np, int Kp,
                  const float* aux, int ldaux, int aux_cols, cudaStream_t st) {
+  if (g_gemm.planes > 0) return tc_gemm(g_gemm.planes, epi, X, ldx, W, bias, Y, ldy, M, Np, Kp, aux, ldaux, aux_cols, g_gemm.scratch, st);
   dim3 grid((unsigned)ceil_div(M, 128), (unsigned)ceil_div(Np, 128));
   switch (epi) {
     case EPI_NONE: k_sgemm<EPI_NONE><<<grid, 256, 0, st>>>(X, ldx, W, bias, Y, ldy, M, Np, Kp, aux, ldaux, aux_cols); break;
@@ -551,13 +558,17 @@ static int geo_backward_inputs(const sdfb200_field_t& f, const FieldPlan& p, con
 }
 
 int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char* blob, const void* table, const sdfb200_field_in_t& in,
-                       const sdfb200_field_out_t& out, float* ws, size_t ws_floats, cudaStream_t st) {
+                       const sdfb200_field_out_t& out, float* ws, size_t ws_floats, cudaStream_t st, int gemm_planes) {
   const int64_t N = in.n_rays * (int64_t)in.n_samples;
   if (N == 0) return 0;
+  struct EngineScope {   // restores the exact-fp32 engine on every exit path
+    ~EngineScope() { g_gemm = {0, nullptr}; }
+  } engine_scope;
   const int64_t chunk = N < kChunkPoints ? N : kChunkPoints;
   FieldWorkspace w;
   make_workspace_plan(f, p, chunk, w);
   if (ws_floats < w.floats_per_chunk) return fail(SDFB200_EWORKSPACE, "workspace too small%s (need %lld floats)", "", (long long)w.floats_per_chunk);
+  g_gemm = {gemm_planes, ws + w.tcw};
 
   const bool want_color = out.rgb != nullptr;
   const bool want_grad = want_color || out.gradients || out.normals || out.alpha;

@@ -132,3 +132,58 @@ def test_field_fp16_table_matches_oracle_on_the_same_quantised_table(precision):
     e64 = o64.get_outputs(o.double(), d.double(), eu[:, :-1].double(), (eu[:, 1:] - eu[:, :-1]).double(), cam, return_alphas=True)
     for key, k in ((H.SDF, "sdf"), (H.RGB, "rgb"), (H.ALPHA, "alphas"), (H.GRADIENT, "gradients")):
         assert_within_noise(out[key], oo[k], e64[k], f"fp16-table/{precision}/{k}", factor=4.0, floor=1e-4 * float(e64[k].abs().max()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# generic tcgen05 Linear (csrc/tc_linear.cu): the GEMM engine of every field shape outside the fused kernel's family
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("planes", [1, 2])
+@pytest.mark.parametrize("epi", [0, 1, 2, 3])
+@pytest.mark.parametrize("M,Kp,Np", [(128, 80, 256), (1000, 384, 272), (333, 256, 16), (4097, 528, 320)])
+def test_tc_linear_matches_fp64(planes, epi, M, Kp, Np):
+    import sdfstudio_b200 as sb
+
+    lib = sb._lib.load()
+    g = torch.Generator().manual_seed(M + Kp + Np + epi)
+    ldx, ldy = Kp + 16, Np + 32
+    X = (torch.randn(M, ldx, generator=g) * 0.5).cuda()
+    W = (torch.randn(Np, Kp, generator=g) / Kp**0.5).cuda()
+    b = (torch.randn(Np, generator=g) * 0.1).cuda()
+    aux = (torch.rand(M, Np, generator=g) * 0.05).cuda()               # "h" values whose softplus' scales the result (epi 3)
+    aux_cols = Np - 16
+    Y = torch.full((M, ldy), float("nan"), device="cuda")
+    scratch = torch.zeros(1 << 18, dtype=torch.uint8, device="cuda")
+    sb._lib.check(lib.sdfb200_debug_tc_linear(planes, epi, X.data_ptr(), ldx, W.data_ptr(), b.data_ptr(), Y.data_ptr(), ldy, M, Np, Kp, aux.data_ptr(),
+                                              Np, aux_cols, scratch.data_ptr(), 0), "debug_tc_linear")
+    torch.cuda.synchronize()
+    z = X[:, :Kp].double() @ W.double().t()
+    if epi != 3:
+        z = z + b.double()
+    if epi == 1:
+        z = torch.nn.functional.softplus(z, beta=100)
+    elif epi == 2:
+        z = torch.relu(z)
+    elif epi == 3:
+        z[:, :aux_cols] = z[:, :aux_cols] * (-torch.expm1(-100.0 * aux.double()[:, :aux_cols]))
+    scale = float((X[:, :Kp].abs().double() @ W.abs().double().t()).max())
+    err = float((Y[:, :Np].double() - z).abs().max()) / scale
+    assert torch.isnan(Y[:, Np:]).all()                                 # nothing written outside [0, Np)
+    assert err < (3e-5 if planes == 2 else 8e-3), f"relative-to-|X||W| error {err:.3e}"
+
+
+@pytest.mark.parametrize("name", ["bakedsdf_small", "volsdf_stock", "angelo_small"])
+def test_generic_shapes_on_the_tensor_core_engine(name):
+    """Field shapes outside the fused family at precision='bf16x3': the generic kernels with tcgen05 GEMMs must sit at the fp32
+    reference's own noise level, like the fused kernel does for neus-facto."""
+    sb, field, rs, out, e64, (o, d, cam, eu, o64) = _run_case(name, "bf16x3")
+    G = load_golden(name)
+    H = sb.FieldHeadNames
+    # floor 3e-4 of the head's scale: the stock 8x256 network chains 16 bf16x3 GEMMs (forward + reverse sweep), each ~2^-16 relative,
+    # and the angelo shape divides sdf differences by 2 delta (numerical gradients)
+    for key, gk in ((H.SDF, "sdf"), (H.RGB, "rgb"), (H.ALPHA, "alphas"), (H.DENSITY, "density"), (H.GRADIENT, "gradients"), (H.NORMAL, "normals")):
+        assert_within_noise(out[key], G[gk], e64[gk], f"{name}/{gk}", factor=4.0, floor=3e-4 * float(e64[gk].abs().max()))
+    w = rs.get_weights_from_alphas(out[H.ALPHA])
+    img = sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, torch.ones(3, device="cuda"))
+    ow, _ = samplers.weights_from_alphas(e64["alphas"][..., 0])
+    orgb = render.render_rgb(e64["rgb"], ow[..., None], torch.ones(3, dtype=torch.float64))
+    assert rel_err(img["rgb"], orgb, 1e-2) < 1e-4
