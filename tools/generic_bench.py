@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--rays", type=int, default=4096)
     ap.add_argument("--samples", type=int, default=128)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--shape", default=None, choices=[None, *SHAPES])
+    ap.add_argument("--precision", default=None, help="only this precision (skips the fp32 reference run and the rgb diff)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     R, S = args.rays, args.samples
@@ -37,7 +39,9 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ref = {}
     for shape, kw in SHAPES.items():
-        for prec in ("fp32", "bf16x3", "bf16"):
+        if args.shape and shape != args.shape:
+            continue
+        for prec in ((args.precision,) if args.precision else ("fp32", "bf16x3", "bf16")):
             torch.manual_seed(0)
             cfg = sb.SDFFieldConfig(grid_layout="torch", precision=prec, **kw)
             sd = sb.SceneContraction(order=float("inf")) if shape == "bakedsdf" else None
@@ -58,7 +62,7 @@ def main():
             rgb = out[sb.FieldHeadNames.RGB]
             if prec == "fp32":
                 ref[shape] = rgb
-            err = float((rgb - ref[shape]).abs().max())
+            err = float((rgb - ref[shape]).abs().max()) if shape in ref else None
             ms = tot / args.steps
             print(json.dumps({"shape": shape, "precision": prec, "rays": R, "samples": S, "field_ms": ms, "rays_per_s": R / ms * 1e3,
                               "max_abs_rgb_diff_vs_fp32": err}))
