@@ -128,22 +128,32 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
     const int row = (warp & 3) * 32 + lane;               // tile row == TMEM lane
     const int q = warp >> 2;
     const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    // register double buffer: the 8 row loads of the NEXT 128-column half are in flight while the current half is converted
+    float4 t[8];
+    auto load_half = [&](int kbase) {
+      const int kcols = a.Kc32 - kbase < 128 ? a.Kc32 - kbase : 128;
+      const int k = kbase + lane * 4;
+      const bool colok = lane * 4 < kcols && k < a.Kvalid;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + warp + 16 * i;
+        t[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (colok && m < a.M) t[i] = __ldg(reinterpret_cast<const float4*>(a.X + m * (long long)a.ldx + k));
+      }
+    };
+    load_half(0);
     for (int kbase = 0; kbase < a.Kc32; kbase += 128) {
       const int kcols = a.Kc32 - kbase < 128 ? a.Kc32 - kbase : 128;          // multiple of 32
-      for (int r = warp; r < 128; r += 16) {
-        const long long m = m0 + r;
-        const int k = kbase + lane * 4;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M && lane * 4 < kcols && k < a.Kvalid) t = __ldg(reinterpret_cast<const float4*>(a.X + m * (long long)a.ldx + k));
-        *reinterpret_cast<float4*>(stg + r * kLdS + lane * 4) = t;
-      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(stg + (warp + 16 * i) * kLdS + lane * 4) = t[i];
+      if (kbase + 128 < a.Kc32) load_half(kbase + 128);
       bar_sync(2, kEpiL);
       for (int g = q; g < kcols / 16; g += 4) {
         float v[16];
 #pragma unroll
         for (int j4 = 0; j4 < 4; ++j4) {
-          const float4 t = *reinterpret_cast<const float4*>(stg + row * kLdS + g * 16 + j4 * 4);
-          v[j4 * 4] = t.x; v[j4 * 4 + 1] = t.y; v[j4 * 4 + 2] = t.z; v[j4 * 4 + 3] = t.w;
+          const float4 u = *reinterpret_cast<const float4*>(stg + row * kLdS + g * 16 + j4 * 4);
+          v[j4 * 4] = u.x; v[j4 * 4 + 1] = u.y; v[j4 * 4 + 2] = u.z; v[j4 * 4 + 3] = u.w;
         }
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -175,35 +185,45 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
         if (a.final_chunk && EPI != TCL_MUL_DSOFTPLUS) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
         const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
-        for (int r = warp; r < 128; r += 16) {
-          const long long m = m0 + r;
-          if (m >= a.M) break;
-          const float4 d4 = *reinterpret_cast<const float4*>(stg + r * kLdS + lane * 4);
-          float y[4] = {d4.x, d4.y, d4.z, d4.w};
-          float* yp = a.Y + m * (long long)a.ldy + a.n0 + n;
-          if (a.accumulate) {
-            const float4 pv = *reinterpret_cast<const float4*>(yp);
-            y[0] += pv.x; y[1] += pv.y; y[2] += pv.z; y[3] += pv.w;
+        // operands that come from global memory (previous partial sums, softplus' source) are fetched for all 8 rows of this warp first
+        const bool want_aux = a.final_chunk && EPI == TCL_MUL_DSOFTPLUS && a.n0 + n < a.aux_cols;
+        float4 pv[8], hv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long m = m0 + warp + 16 * i;
+          pv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          hv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < a.M) {
+            if (a.accumulate) pv[i] = *reinterpret_cast<const float4*>(a.Y + m * (long long)a.ldy + a.n0 + n);
+            if (want_aux) hv[i] = __ldg(reinterpret_cast<const float4*>(a.aux + m * (long long)a.ldaux + a.n0 + n));
           }
-          if (a.final_chunk) {
-            if (EPI == TCL_MUL_DSOFTPLUS) {
-              if (a.n0 + n < a.aux_cols) {                  // aux_cols and n are multiples of 4 apart from the tail handled per element
-                const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.aux + m * (long long)a.ldaux + a.n0 + n));
-                const float hh[4] = {h4.x, h4.y, h4.z, h4.w};
+        }
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  if (a.n0 + n + j < a.aux_cols) y[j] *= tcl_dsoftplus_from_h(hh[j]);
-              }
-            } else {
+        for (int i = 0; i < 8; ++i) {
+          const int r = warp + 16 * i;
+          const long long m = m0 + r;
+          if (m < a.M) {
+            const float4 d4 = *reinterpret_cast<const float4*>(stg + r * kLdS + lane * 4);
+            float y[4] = {d4.x + pv[i].x, d4.y + pv[i].y, d4.z + pv[i].z, d4.w + pv[i].w};
+            if (a.final_chunk) {
+              if (EPI == TCL_MUL_DSOFTPLUS) {
+                if (want_aux) {
+                  const float hh[4] = {hv[i].x, hv[i].y, hv[i].z, hv[i].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                y[j] += b4[j];
-                if (EPI == TCL_SOFTPLUS) y[j] = tcl_softplus100(y[j]);
-                if (EPI == TCL_RELU) y[j] = fmaxf(y[j], 0.f);
+                  for (int j = 0; j < 4; ++j)
+                    if (a.n0 + n + j < a.aux_cols) y[j] *= tcl_dsoftplus_from_h(hh[j]);
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  y[j] += b4[j];
+                  if (EPI == TCL_SOFTPLUS) y[j] = tcl_softplus100(y[j]);
+                  if (EPI == TCL_RELU) y[j] = fmaxf(y[j], 0.f);
+                }
               }
             }
+            *reinterpret_cast<float4*>(a.Y + m * (long long)a.ldy + a.n0 + n) = make_float4(y[0], y[1], y[2], y[3]);
           }
-          *reinterpret_cast<float4*>(yp) = make_float4(y[0], y[1], y[2], y[3]);
         }
       }
       bar_sync(2, kEpiL);

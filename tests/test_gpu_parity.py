@@ -335,13 +335,13 @@ def test_large_batch_crosses_chunks():
     import sdfstudio_b200 as sb
 
     spec, kw, o, d, cam, nears, fars, oracle, field = build_case("neusfacto_c1_init")
-    R, S = 1100, 64  # 70400 points > 65536
+    R, S = 1300, 64  # 83200 points > the 75776-point chunk (field_plan.h kChunkPoints); rays 1160..1210 straddle the boundary
     o, d, cam = cases.synthetic_rays(R, 123)
     nears, fars = torch.full((R, 1), 0.5), torch.full((R, 1), 4.5)
     rb = make_bundle(o, d, cam, nears, fars)
     rs = sb.UniformSampler(num_samples=S).eval()(rb)
     big = field(rs, return_alphas=True)
-    sl = slice(1000, 1050)
+    sl = slice(1160, 1210)
     rb2 = make_bundle(o[sl], d[sl], cam[sl], nears[sl], fars[sl])
     small = field(sb.UniformSampler(num_samples=S).eval()(rb2), return_alphas=True)
     for k in (sb.FieldHeadNames.RGB, sb.FieldHeadNames.SDF, sb.FieldHeadNames.ALPHA, sb.FieldHeadNames.GRADIENT):
