@@ -83,12 +83,38 @@ class Sampler(nn.Module):
         return self.generate_ray_samples(*args, **kwargs)
 
 
-class SpacedSampler(Sampler):
-    """ray_samplers.py:55-127.  ``spacing`` names one of the reference's (spacing_fn, spacing_fn_inv) pairs."""
+def identify_spacing(spacing_fn, spacing_fn_inv=None) -> str:
+    """Name of the (spacing_fn, spacing_fn_inv) pair: the kernels implement the reference's five spacings (ray_samplers.py:130-247)
+    in-register, so a callable is recognised by evaluating it on a few probe values.  Anything else is refused (there is no
+    PyTorch fallback path in this package)."""
+    if isinstance(spacing_fn, str):
+        if spacing_fn not in _SPACING_TORCH:
+            raise ValueError(f"unknown spacing {spacing_fn!r}; one of {sorted(_SPACING_TORCH)}")
+        return spacing_fn
+    probe = torch.tensor([0.25, 0.5, 0.75, 1.0, 1.5, 2.0, 4.0, 9.0], dtype=torch.float64)
+    try:
+        got = torch.as_tensor(spacing_fn(probe), dtype=torch.float64)
+    except Exception as e:  # noqa: BLE001
+        raise NotImplementedError(f"spacing_fn could not be evaluated on a probe tensor: {e}") from e
+    for name, (fn, inv) in _SPACING_TORCH.items():
+        if torch.allclose(got, fn(probe), rtol=1e-12, atol=0):
+            if spacing_fn_inv is not None:
+                back = torch.as_tensor(spacing_fn_inv(fn(probe)), dtype=torch.float64)
+                if not torch.allclose(back, probe, rtol=1e-9, atol=0):
+                    raise ValueError(f"spacing_fn_inv is not the inverse of the {name!r} spacing_fn")
+            return name
+    raise NotImplementedError("SpacedSampler: only the reference's spacings (uniform, 1/x, sqrt, log, uniform+lindisp piecewise) run in the "
+                              "kernels; this spacing_fn is none of them")
 
-    def __init__(self, spacing: str = "uniform", num_samples: Optional[int] = None, train_stratified=True, single_jitter=False) -> None:
+
+class SpacedSampler(Sampler):
+    """ray_samplers.py:55-127, same constructor: ``spacing_fn`` / ``spacing_fn_inv`` callables (recognised by probing, see
+    ``identify_spacing``); a spacing NAME ("uniform", "lindisp", "sqrt", "log", "piecewise") is accepted in place of ``spacing_fn``."""
+
+    def __init__(self, spacing_fn, spacing_fn_inv=None, num_samples: Optional[int] = None, train_stratified=True, single_jitter=False) -> None:
         super().__init__(num_samples=num_samples)
-        self.spacing = spacing
+        self.spacing = identify_spacing(spacing_fn, spacing_fn_inv)
+        self.spacing_fn, self.spacing_fn_inv = _SPACING_TORCH[self.spacing]
         self.train_stratified = train_stratified
         self.single_jitter = single_jitter
 
@@ -114,27 +140,27 @@ class SpacedSampler(Sampler):
 
 class UniformSampler(SpacedSampler):
     def __init__(self, num_samples=None, train_stratified=True, single_jitter=False) -> None:
-        super().__init__("uniform", num_samples, train_stratified, single_jitter)
+        super().__init__("uniform", None, num_samples, train_stratified, single_jitter)
 
 
 class LinearDisparitySampler(SpacedSampler):
     def __init__(self, num_samples=None, train_stratified=True, single_jitter=False) -> None:
-        super().__init__("lindisp", num_samples, train_stratified, single_jitter)
+        super().__init__("lindisp", None, num_samples, train_stratified, single_jitter)
 
 
 class SqrtSampler(SpacedSampler):
     def __init__(self, num_samples=None, train_stratified=True, single_jitter=False) -> None:
-        super().__init__("sqrt", num_samples, train_stratified, single_jitter)
+        super().__init__("sqrt", None, num_samples, train_stratified, single_jitter)
 
 
 class LogSampler(SpacedSampler):
     def __init__(self, num_samples=None, train_stratified=True, single_jitter=False) -> None:
-        super().__init__("log", num_samples, train_stratified, single_jitter)
+        super().__init__("log", None, num_samples, train_stratified, single_jitter)
 
 
 class UniformLinDispPiecewiseSampler(SpacedSampler):
     def __init__(self, num_samples=None, train_stratified=True, single_jitter=False) -> None:
-        super().__init__("piecewise", num_samples, train_stratified, single_jitter)
+        super().__init__("piecewise", None, num_samples, train_stratified, single_jitter)
 
 
 def _pdf_sample(spacing_bins, weights2d, num_samples, histogram_padding, include_original, training_jitter, single_jitter, eps=1e-5,

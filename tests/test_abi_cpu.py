@@ -147,3 +147,60 @@ def test_reference_checkpoint_layout_loads():
     torch_layout, _ = _product_field_cpu("neusfacto_c1", layout="torch")
     with pytest.raises(ValueError):
         checkpoint.load_field_checkpoint(torch_layout, ckpt)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the Python mirrors keep the reference's constructor signatures and config defaults (fixture minted from the unmodified
+# reference by oracle/make_golden_api.py)
+# ---------------------------------------------------------------------------------------------------------------
+def test_mirror_signatures_and_config_defaults_match_reference():
+    import dataclasses
+    import inspect
+    import json
+
+    import sdfstudio_b200 as sb
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_api.json")) as fh:
+        ref = json.load(fh)
+
+    def plain(v):
+        if isinstance(v, (int, float, str, bool)) or v is None:
+            return v
+        if isinstance(v, (tuple, list)):
+            return [plain(x) for x in v]
+        return f"<{type(v).__name__}>"
+
+    mine_cfg = {f.name: plain(f.default) for f in dataclasses.fields(sb.SDFFieldConfig) if f.name != "_target" and f.default is not dataclasses.MISSING}
+    b200_knobs = {"grid_layout", "precision", "table_dtype"}
+    assert {k: v for k, v in mine_cfg.items() if k not in b200_knobs} == ref["SDFFieldConfig"]
+    problems = []
+    for name, sig in ref.items():
+        if name == "SDFFieldConfig":
+            continue
+        cls = getattr(sb, name, None) or getattr(sb.sdf_field, name, None)
+        assert cls is not None, f"{name} is not mirrored"
+        params = [(n, p) for n, p in inspect.signature(cls.__init__).parameters.items() if n not in ("self", "kwargs", "args")]
+        mine = [[n, None if p.default is inspect.Parameter.empty else plain(p.default)] for n, p in params]
+        # every reference parameter exists, in the same order, with the same default (extra trailing B200 keyword arguments are allowed)
+        if mine[: len(sig)] != sig:
+            problems.append((name, mine[: len(sig)], sig))
+    assert not problems, problems
+
+
+def test_spaced_sampler_accepts_the_reference_callables():
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200.ray_samplers import identify_spacing
+
+    # the lambdas exactly as the reference's subclasses write them (ray_samplers.py:130-247)
+    assert identify_spacing(lambda x: x, lambda x: x) == "uniform"
+    assert identify_spacing(lambda x: 1 / x, lambda x: 1 / x) == "lindisp"
+    assert identify_spacing(torch.sqrt, lambda x: x**2) == "sqrt"
+    assert identify_spacing(torch.log, torch.exp) == "log"
+    assert identify_spacing(lambda x: torch.where(x < 1, x / 2, 1 - 1 / (2 * x)), lambda x: torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))) == "piecewise"
+    s = sb.SpacedSampler(spacing_fn=torch.sqrt, spacing_fn_inv=lambda x: x**2, num_samples=8)
+    assert s.spacing == "sqrt" and s.num_samples == 8
+    assert sb.UniformLinDispPiecewiseSampler(num_samples=4).spacing == "piecewise"
+    with pytest.raises(NotImplementedError):
+        sb.SpacedSampler(spacing_fn=lambda x: x**3, spacing_fn_inv=lambda x: x ** (1 / 3))
+    with pytest.raises(ValueError):
+        sb.SpacedSampler(spacing_fn=torch.sqrt, spacing_fn_inv=lambda x: x)

@@ -99,7 +99,7 @@ def test_field_matches_reference_golden(name):
     G = load_golden(name)
     spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name)
     rb = make_bundle(o, d, cam, nears, fars)
-    sampler = sb.SpacedSampler(kw.get("spacing", "uniform"), num_samples=kw["S"]).eval()
+    sampler = sb.SpacedSampler(kw.get("spacing", "uniform"), None, num_samples=kw["S"]).eval()
     rs = sampler(rb)
     assert torch.equal(sb.rays.spacing_bins_of(rs).cpu(), G["spacing_bins"])  # bit-exact bin edges
     assert torch.equal(sb.rays.bins_of(rs).cpu(), G["euclid_bins"])
