@@ -301,10 +301,14 @@ int sdfb200_render_backward(const float* weights, const float* rgb, const float*
                             const float* g_rgb, const float* g_depth, const float* g_normal, const float* g_accumulation,
                             const float* g_weights_in, float* g_weights, float* g_rgb_samples, float* g_normal_samples, void* stream);
 
-/* backward of sdfb200_weights_from_alphas (from_density = 0; g_last_transmittance [R] = gradient of transmittance[:, -1],
- * may be NULL) or sdfb200_weights_from_density (from_density = 1): g_weights [R,S] -> g_in [R,S]. */
+/* backward of sdfb200_weights_from_alphas (from_density = 0) or sdfb200_weights_from_density (from_density = 1):
+ * g_weights [R,S] (+ the gradient of the returned transmittance) -> g_in [R,S].  g_transmittance may be NULL; otherwise
+ * g_transmittance_cols = 1 (alphas only: [R], gradient of transmittance[:, -1] = bg_transmittance, models/neus.py:101) or the
+ * full width of the transmittance output ([R,S+1] for alphas, [R,S] for densities; models/volsdf.py:67-68 back-propagates
+ * through transmittance[:, -1] of the density form). */
 int sdfb200_weights_backward(const float* alphas_or_density, const float* euclid_bins, int32_t from_density, int64_t n_rays,
-                             int32_t n_samples, const float* g_weights, const float* g_last_transmittance, float* g_in, void* stream);
+                             int32_t n_samples, const float* g_weights, const float* g_transmittance, int32_t g_transmittance_cols,
+                             float* g_in, void* stream);
 
 
 /* ---------------------------------------------------------------------------------------------------------------*/

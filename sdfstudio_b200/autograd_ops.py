@@ -14,8 +14,8 @@ def needs_grad(*ts) -> bool:
 
 
 class WeightsFromAlphasFn(torch.autograd.Function):
-    """alphas [R,S] -> weights [R,S], transmittance [R,S+1] (rays.py:194-230).  Only transmittance[:, -1] (bg_transmittance,
-    models/neus.py:101) carries a gradient back; the other columns are not used by any loss of the reference."""
+    """alphas [R,S] -> weights [R,S], transmittance [R,S+1] (rays.py:194-230).  Gradients flow back through the weights and
+    through every transmittance column (bg_transmittance = transmittance[:, -1], models/neus.py:101)."""
 
     @staticmethod
     def forward(ctx, alphas):
@@ -35,15 +35,17 @@ class WeightsFromAlphasFn(torch.autograd.Function):
         (a,) = ctx.saved_tensors
         R, S = a.shape
         g_w = _lib.f32c(g_w) if g_w is not None else torch.zeros_like(a)
-        g_last = _lib.f32c(g_T[:, -1]) if g_T is not None else None
+        g_T = _lib.f32c(g_T) if g_T is not None else None
         g_a = torch.empty_like(a)
-        _lib.check(lib.sdfb200_weights_backward(_lib.ptr(a), None, 0, R, S, _lib.ptr(g_w), _lib.ptr(g_last), _lib.ptr(g_a), _lib.stream_ptr()),
+        _lib.check(lib.sdfb200_weights_backward(_lib.ptr(a), None, 0, R, S, _lib.ptr(g_w), _lib.ptr(g_T), S + 1, _lib.ptr(g_a), _lib.stream_ptr()),
                    "sdfb200_weights_backward")
         return g_a
 
 
 class WeightsFromDensityFn(torch.autograd.Function):
-    """densities [R,S], euclidean bins [R,S+1] -> weights [R,S], transmittance [R,S] (rays.py:131-192); gradient to densities."""
+    """densities [R,S], euclidean bins [R,S+1] -> weights [R,S], transmittance [R,S] (rays.py:131-192).  Gradients flow to the
+    densities through the weights AND the transmittance (VolSDF composites the background model with transmittance[:, -1],
+    models/volsdf.py:67-68 + base_surface_model.py:329)."""
 
     @staticmethod
     def forward(ctx, density, bins):
@@ -55,7 +57,6 @@ class WeightsFromDensityFn(torch.autograd.Function):
         _lib.check(lib.sdfb200_weights_from_density(_lib.ptr(d), _lib.ptr(bins), R, S, _lib.ptr(w), _lib.ptr(T), _lib.stream_ptr()),
                    "sdfb200_weights_from_density")
         ctx.save_for_backward(d, bins)
-        ctx.mark_non_differentiable(T)
         return w, T
 
     @staticmethod
@@ -64,9 +65,10 @@ class WeightsFromDensityFn(torch.autograd.Function):
         lib = _lib.load()
         d, bins = ctx.saved_tensors
         R, S = d.shape
-        g_w = _lib.f32c(g_w)
+        g_w = _lib.f32c(g_w) if g_w is not None else torch.zeros_like(d)
+        g_T = _lib.f32c(g_T) if g_T is not None else None
         g_d = torch.empty_like(d)
-        _lib.check(lib.sdfb200_weights_backward(_lib.ptr(d), _lib.ptr(bins), 1, R, S, _lib.ptr(g_w), None, _lib.ptr(g_d), _lib.stream_ptr()),
+        _lib.check(lib.sdfb200_weights_backward(_lib.ptr(d), _lib.ptr(bins), 1, R, S, _lib.ptr(g_w), _lib.ptr(g_T), S, _lib.ptr(g_d), _lib.stream_ptr()),
                    "sdfb200_weights_backward")
         return g_d, None
 
@@ -170,6 +172,6 @@ class RenderAlphasFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             g_a = torch.empty_like(a)
             g_last = _lib.f32c(g_bgT) if g_bgT is not None else None
-            _lib.check(lib.sdfb200_weights_backward(_lib.ptr(a), None, 0, R, S, _lib.ptr(g_w), _lib.ptr(g_last), _lib.ptr(g_a), _lib.stream_ptr()),
+            _lib.check(lib.sdfb200_weights_backward(_lib.ptr(a), None, 0, R, S, _lib.ptr(g_w), _lib.ptr(g_last), 1, _lib.ptr(g_a), _lib.stream_ptr()),
                        "sdfb200_weights_backward")
         return g_a, g_rgb_s, g_nrm_s, None, None, None

@@ -60,9 +60,12 @@ __global__ void __launch_bounds__(256) k_render_bwd(const RenderBwdArgs a) {
 
 // weights_i = alpha_i T_i,  T_i = prod_{j<i} f_j,  f_j = 1 - alpha_j + 1e-7 (rays.py:204-206)     [mode 0]
 // weights_i = (1 - f_i) T_i, f_i = exp(-delta_i sigma_i), T_i = exp(-sum_{j<i} delta_j sigma_j) (rays.py:131-180)  [mode 1]
-//   dL/dalpha_i = gw_i T_i - (sum_{k>i} gw_k w_k + gT_S T_S) / f_i ;      dL/dsigma_i = delta_i f_i dL/dalpha_i
+//   dL/dalpha_i = gw_i T_i - (sum_{k>i} (gw_k w_k + gT_k T_k) + gT_S T_S) / f_i ;      dL/dsigma_i = delta_i f_i dL/dalpha_i
+// g_T: gradient of the returned transmittance, gt_cols = 0 (none), 1 (only the last column, [R]: bg_transmittance of
+// models/neus.py:101) or the full width ([R,S+1] for alphas, [R,S] for densities: volsdf.py:67-68 reads transmittance[:, -1],
+// the transmittance BEFORE the last sample).
 __global__ void __launch_bounds__(256) k_weights_bwd(const float* __restrict__ in, const float* __restrict__ eu, int from_density, int64_t R, int S,
-                                                     const float* __restrict__ g_weights, const float* __restrict__ g_last_T,
+                                                     const float* __restrict__ g_weights, const float* __restrict__ g_T, int gt_cols,
                                                      float* __restrict__ g_in) {
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -104,7 +107,8 @@ __global__ void __launch_bounds__(256) k_weights_bwd(const float* __restrict__ i
         al = 1.0f - f;
       }
       const float gw = on ? g_weights[r * S + s] : 0.f;
-      const double u = (double)gw * (double)(al * T);
+      const float gt = (on && (from_density ? gt_cols >= 1 : gt_cols > 1)) ? g_T[r * gt_cols + s] : 0.f;
+      const double u = (double)gw * (double)(al * T) + (double)gt * (double)T;
       double uincl = u;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(256) k_weights_bwd(const float* __restrict__ i
       }
       if (pass == 1 && on) {
         const double suffix = U - (carryU + uincl);                       // sum_{k>s} gw_k w_k
-        const double tail = suffix + (g_last_T ? (double)g_last_T[r] * TS : 0.0);
+        const double tail = suffix + ((!from_density && gt_cols >= 1) ? (double)g_T[r * gt_cols + (gt_cols - 1)] * TS : 0.0);
         if (!from_density) g_in[r * S + s] = (float)((double)gw * (double)T - tail / (double)f);
         else g_in[r * S + s] = (float)((double)delta * ((double)gw * (double)T * (double)f - tail));
       }
@@ -147,13 +151,17 @@ extern "C" int sdfb200_render_backward(const float* weights, const float* rgb, c
 }
 
 extern "C" int sdfb200_weights_backward(const float* alphas_or_density, const float* euclid_bins, int32_t from_density, int64_t n_rays,
-                                        int32_t n_samples, const float* g_weights, const float* g_last_transmittance, float* g_in, void* stream) {
+                                        int32_t n_samples, const float* g_weights, const float* g_transmittance, int32_t g_transmittance_cols,
+                                        float* g_in, void* stream) {
   SDFB_REQUIRE(n_rays >= 0 && n_samples >= 1, "bad sizes");
   if (n_rays == 0) return 0;
   SDFB_REQUIRE(alphas_or_density && g_weights && g_in, "NULL pointer");
-  if (from_density) SDFB_REQUIRE(euclid_bins != nullptr && g_last_transmittance == nullptr, "density mode needs bins and has no transmittance gradient");
+  if (from_density) SDFB_REQUIRE(euclid_bins != nullptr, "density mode needs bins");
+  const int gt_cols = g_transmittance ? g_transmittance_cols : 0;
+  SDFB_REQUIRE(gt_cols == 0 || (gt_cols == 1 && !from_density) || gt_cols == n_samples + (from_density ? 0 : 1),
+               "g_transmittance_cols must be 1 (alphas: last column only) or the width of the transmittance output");
   k_weights_bwd<<<(unsigned)ceil_div(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(alphas_or_density, euclid_bins, from_density, n_rays, n_samples,
-                                                                                 g_weights, g_last_transmittance, g_in);
+                                                                                 g_weights, g_transmittance, gt_cols, g_in);
   SDFB_LAUNCHED("k_weights_bwd");
   return 0;
 }

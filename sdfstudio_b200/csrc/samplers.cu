@@ -227,17 +227,22 @@ __device__ __forceinline__ float volsdf_dstar(const float* e, const float* sd, i
 __device__ float volsdf_error_bound(const float* e, const float* sd, int S, float beta) {
   double integ = 0.0, errint = 0.0;
   float best = -INFINITY;
+  bool saw_nan = false;
   const float b2 = __fmul_rn(4.0f, __fmul_rn(beta, beta));
   for (int i = 0; i < S; ++i) {
     const float delta = __fsub_rn(e[i + 1], e[i]);
     const float ds = volsdf_dstar(e, sd, i < S - 1 ? i : S - 2);
     const float err_sec = __fdiv_rn(__fmul_rn(expf(__fdiv_rn(-ds, beta)), __fmul_rn(delta, delta)), b2);
     errint += (double)err_sec;
-    const float bound = __fmul_rn(__fsub_rn(fminf(expf((float)errint), 1.0e6f), 1.0f), expf(-(float)integ));
-    best = fmaxf(best, bound);
+    // torch.clamp and .max(-1) propagate NaN (a slightly negative Heron area gives sqrt(<0) = NaN d_star in the reference):
+    // fminf / fmaxf would drop it, so it is carried explicitly -- a NaN bound leaves beta untouched, as in the reference
+    const float ef = expf((float)errint);
+    const float bound = __fmul_rn(__fsub_rn(ef != ef ? ef : fminf(ef, 1.0e6f), 1.0f), expf(-(float)integ));
+    if (bound != bound) saw_nan = true;
+    else best = fmaxf(best, bound);
     integ += (double)__fmul_rn(delta, laplace_density(sd[i], beta));
   }
-  return best;
+  return saw_nan ? __int_as_float(0x7fc00000) : best;
 }
 
 __global__ void __launch_bounds__(64) k_volsdf_step(const float* __restrict__ eu, const float* __restrict__ sdf, const float* __restrict__ beta0p,

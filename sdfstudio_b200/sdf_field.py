@@ -308,7 +308,7 @@ class SDFField(nn.Module):
         nbytes = lib.sdfb200_field_packed_bytes(desc)
         if nbytes == 0:
             _lib.check(-1, "sdfb200_field_packed_bytes")
-        if self._packed is None or self._packed.numel() != nbytes:
+        if self._packed is None or self._packed.numel() != nbytes or self._packed.device != params[0].device:
             self._packed = torch.empty(nbytes, dtype=torch.uint8, device=params[0].device)
         fp = _lib.FieldParams()
         keep = []
@@ -342,7 +342,7 @@ class SDFField(nn.Module):
         nbytes = lib.sdfb200_field_workspace_bytes(desc, n_points)
         if nbytes == 0:
             _lib.check(-1, "sdfb200_field_workspace_bytes")
-        if self._workspace is None or self._workspace.numel() < nbytes:
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != self.aabb.device:
             self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.aabb.device)
         return self._workspace
 

@@ -141,6 +141,24 @@ def test_weights_and_render_backward():
     assert _maxrel(wc[..., 0], wd) < 1e-5
     gd = torch.autograd.grad((wc * c_w.cuda()).sum(), dc)[0]
     assert _maxrel(gd, gd_r) < 2e-4
+    # transmittance gradient of the density form: VolSDF composites its background model with transmittance[:, -1]
+    # (models/volsdf.py:67-68 + base_surface_model.py:329); every column must back-propagate, not only the weights
+    c_T = torch.randn(R, S, generator=g)
+    gd_rT = torch.autograd.grad((wd * c_w[..., 0].double()).sum() + (Tr * c_T.double()).sum() + 3.0 * Tr[:, -1].sum(), d64)[0]
+    dc2 = dens.cuda().requires_grad_(True)
+    wc2, Tc2 = weights_from_density(bins.cuda(), dc2, True)
+    assert _maxrel(Tc2[..., 0], Tr) < 1e-5
+    gdT = torch.autograd.grad((wc2 * c_w.cuda()).sum() + (Tc2[..., 0] * c_T.cuda()).sum() + 3.0 * Tc2[:, -1].sum(), dc2)[0]
+    assert _maxrel(gdT, gd_rT) < 2e-4
+    # ... and the alpha form through interior transmittance columns
+    a64b = alphas.double().requires_grad_(True)
+    wb, Tb = _ref_weights_alpha(a64b[..., 0])
+    c_T1 = torch.randn(R, S + 1, generator=g)
+    ga_rT = torch.autograd.grad((Tb * c_T1.double()).sum() + (wb * c_w[..., 0].double()).sum(), a64b)[0]
+    ac3 = alphas.cuda().requires_grad_(True)
+    w3, T3 = weights_from_alphas(ac3, True)
+    gaT = torch.autograd.grad((T3[..., 0] * c_T1.cuda()).sum() + (w3 * c_w.cuda()).sum(), ac3)[0]
+    assert _maxrel(gaT[..., 0].cpu()[~sat], ga_rT[..., 0][~sat]) < 2e-4
 
 
 # ------------------------------------------------------------------------------------------------------------------ SDFField step
