@@ -261,6 +261,30 @@ int sdfb200_render(const float* weights, const float* rgb, const float* normals,
 int sdfb200_render_alphas(const float* alphas, const float* rgb, const float* normals, const float* euclid_bins,
                           const float* bg, int32_t bg_mode, int32_t clamp01, int64_t n_rays, int32_t n_samples,
                           float* weights, float* bg_transmittance, const sdfb200_render_out_t* out, void* stream);
+/* SDFField.get_outputs + weights + the four renderers in ONE call: what SurfaceModel.get_outputs does between the sampler and
+ * the losses (models/base_surface_model.py:292-365 with models/neus.py:85-116 or models/volsdf.py:62-87).  from_density = 0:
+ * NeuS alphas -> get_weights_and_transmittance_from_alphas (rays.py:194-230); 1: Laplace density -> get_weights_and_transmittance
+ * (rays.py:131-192).  The neus-facto shape family at a tensor-core precision with 128 % n_samples == 0 runs as one fused
+ * kernel (compositing in registers, no per-sample round trip through HBM); every other case is composed inside the
+ * library from sdfb200_field_forward + the compositing kernels, with identical results.  `sample_out` (may be NULL) selects
+ * per-sample heads to materialise as well (weights_list / eikonal consumers); `weights` [R,S], `bg_transmittance` [R] optional.
+ * out.depth is the 'expected' depth; with clip_depth != 0 it is clipped to the batch-global [steps.min(), steps.max()]
+ * (renderers.py:257) at the end of the call; out.steps_minmax [2] must be pre-set to {+inf, -inf}. */
+typedef struct sdfb200_field_render {
+  int32_t from_density;
+  int32_t bg_mode;            /* SDFB200_BG_* */
+  int32_t clamp01;            /* eval-mode clamp of rgb (renderers.py:116-117) */
+  int32_t clip_depth;
+  const float* bg;            /* [3] (BG_COLOR) or [R,3] (BG_PER_RAY); unused for BG_LAST_SAMPLE */
+  float* weights;             /* [R,S] or NULL */
+  float* bg_transmittance;    /* [R]   or NULL: transmittance[:, -1] */
+  sdfb200_render_out_t out;
+} sdfb200_field_render_t;
+size_t sdfb200_field_render_workspace_bytes(const sdfb200_field_t* f, int64_t n_rays, int32_t n_samples);
+int sdfb200_field_render(const sdfb200_field_t* f, const void* packed, const void* table, const sdfb200_field_in_t* in,
+                         const sdfb200_field_out_t* sample_out, const sdfb200_field_render_t* render, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
 /* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
 int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
 
@@ -316,28 +340,9 @@ int sdfb200_version(void);
 const char* sdfb200_last_error_string(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t sdfb200_launch_count(void);
-/* sizeof() of the ABI structs (0 grid, 1 field, 2 field_params, 3 field_in, 4 field_out, 5 render_out): lets a binding
+/* sizeof() of the ABI structs (0 grid, 1 field, 2 field_params, 3 field_in, 4 field_out, 5 render_out, 6 field_render): lets a binding
  * verify its struct mirrors before the first call. */
 size_t sdfb200_struct_size(int32_t which);
-
-/* ---------------------------------------------------------------------------------------------------------------
- * Debug / validation hook (no reference counterpart): one CTA computes D[128,Np] = A[128,K] W[N,K]^T with the tcgen05
- * machinery of the fused field kernel (bf16 split planes, SS- or TS-mode A operand, bulk-copy weight ring).
- * K % 32 == 0, K <= 256, N <= 256, Np = N rounded up to 16.  scratch: >= (K/32)*planes*Np*64 bytes.
- * ------------------------------------------------------------------------------------------------------------- */
-int sdfb200_debug_tc_gemm(const float* A, const float* W, int32_t K, int32_t N, int32_t mode_ts, int32_t planes, float* D,
-                          void* scratch, void* stream);
-
-/* Building-block test of the generic tcgen05 Linear (csrc/tc_linear.cu): Y[M, Np] = epi(X[M, Kp] W[Np, Kp]^T + bias) with
- * epi 0 none / 1 softplus(beta 100) / 2 relu / 3 multiply by softplus'(aux) (no bias); planes 1 = bf16, 2 = bf16x3.
- * All dims padded to 16; scratch >= 256 KiB. */
-int sdfb200_debug_tc_linear(int32_t planes, int32_t epi, const float* X, int32_t ldx, const float* W, const float* bias, float* Y,
-                            int32_t ldy, int64_t M, int32_t Np, int32_t Kp, const float* aux, int32_t ldaux, int32_t aux_cols,
-                            void* scratch, void* stream);
-
-/* debug: copies the 16x32 clock64 phase stamps recorded by the fused tensor-core kernel when the environment variable
- * SDFB200_TC_TIMING is set (CTA 0, first 16 tiles) into a HOST buffer of 512 int64. */
-int sdfb200_debug_tc_timing(long long* host_out_512);
 
 #ifdef __cplusplus
 }

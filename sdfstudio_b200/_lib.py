@@ -69,6 +69,11 @@ class RenderOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("rgb", "depth", "normal", "accumulation", "steps_minmax")]
 
 
+class FieldRender(C.Structure):
+    _fields_ = [("from_density", C.c_int32), ("bg_mode", C.c_int32), ("clamp01", C.c_int32), ("clip_depth", C.c_int32), ("bg", C.c_void_p),
+                ("weights", C.c_void_p), ("bg_transmittance", C.c_void_p), ("out", RenderOut)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -86,7 +91,6 @@ _PROTOS = {
     "sdfb200_generate_rays": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "sdfb200_collide": (C.c_int, [_vp, _vp, _i64, _i32, C.POINTER(C.c_float), _f32, _vp, _vp, _vp]),
     "sdfb200_lattice_points": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int32), _i64, _i64, _vp, _vp]),
-    "sdfb200_debug_tc_linear": (C.c_int, [_i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
     "sdfb200_field_packed_bytes": (_sz, [C.POINTER(FieldDesc)]),
     "sdfb200_field_pack": (C.c_int, [C.POINTER(FieldDesc), C.POINTER(FieldParams), _vp, _vp]),
     "sdfb200_field_workspace_bytes": (_sz, [C.POINTER(FieldDesc), _i64]),
@@ -106,10 +110,35 @@ _PROTOS = {
     "sdfb200_render": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, C.POINTER(RenderOut), _vp]),
     "sdfb200_render_alphas": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, C.POINTER(RenderOut), _vp]),
     "sdfb200_depth_clip": (C.c_int, [_vp, _vp, _i64, _vp]),
-    "sdfb200_debug_tc_timing": (C.c_int, [_vp]),
-    "sdfb200_debug_tc_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+    "sdfb200_field_render_workspace_bytes": (_sz, [C.POINTER(FieldDesc), _i64, _i32]),
+    "sdfb200_field_render": (C.c_int, [C.POINTER(FieldDesc), _vp, _vp, C.POINTER(FieldIn), C.POINTER(FieldOut), C.POINTER(FieldRender), _vp, _sz, _vp]),
 }
 EXPORTED_SYMBOLS = tuple(_PROTOS)
+# validation hooks of the tcgen05 building blocks: libsdfb200_dbg.so only (include/sdfb200_debug.h), never loaded by the product
+_DEBUG_PROTOS = {
+    "sdfb200_debug_tc_linear": (C.c_int, [_i32, _i32, _vp, _i32, _vp, _vp, _vp, _i32, _i64, _i32, _i32, _vp, _i32, _i32, _vp, _vp]),
+    "sdfb200_debug_tc_gemm": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
+}
+_dbg = None
+
+
+def load_debug():
+    """libsdfb200_dbg.so = the product objects + the building-block test hooks (tests/test_gpu_tc.py)."""
+    global _dbg
+    if _dbg is None:
+        path = os.path.join(HERE, "libsdfb200_dbg.so")
+        if not os.path.exists(path):
+            from . import build as _build
+
+            _build.build(force=True)
+        lib = C.CDLL(path)
+        for name, (res, args) in _DEBUG_PROTOS.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        lib.sdfb200_last_error_string.restype = C.c_char_p
+        _dbg = lib
+    return _dbg
 
 
 class Sdfb200Error(RuntimeError):
@@ -133,7 +162,7 @@ def load():
             fn = getattr(lib, name)
             fn.restype = res
             fn.argtypes = args
-        for which, st in enumerate((GridDesc, FieldDesc, FieldParams, FieldIn, FieldOut, RenderOut)):
+        for which, st in enumerate((GridDesc, FieldDesc, FieldParams, FieldIn, FieldOut, RenderOut, FieldRender)):
             if lib.sdfb200_struct_size(which) != C.sizeof(st):
                 raise Sdfb200Error(f"ABI mismatch: sizeof({st.__name__}) = {C.sizeof(st)} but the library says {lib.sdfb200_struct_size(which)}")
         _lib = lib

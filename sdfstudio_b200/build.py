@@ -6,17 +6,19 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdfb200.so")
-SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "tc_test.cu", "tc_linear.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
+LIB_DEBUG = os.path.join(HERE, "libsdfb200_dbg.so")   # product objects + the building-block validation hooks (tests only)
+SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "tc_linear.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
+DEBUG_SOURCES = ["tc_test.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
          "-Xptxas", "-v"]
 
 
 def _stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(LIB_DEBUG):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sdfb200.h")]
+    t = min(os.path.getmtime(LIB), os.path.getmtime(LIB_DEBUG))
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", h) for h in ("sdfb200.h", "sdfb200_debug.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -29,9 +31,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
-    for s in SOURCES:
+    dbg_objs = []
+    for s in SOURCES + DEBUG_SOURCES:
         o = os.path.join(objdir, s.replace(".cu", ".o"))
-        objs.append(o)
+        (dbg_objs if s in DEBUG_SOURCES else objs).append(o)
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
@@ -45,6 +48,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(log))
     subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-o", LIB_DEBUG, *objs, *dbg_objs, "-lcudart"])
     return LIB
 
 

@@ -2,6 +2,8 @@
 #include "common.cuh"
 #include "field_plan.h"
 
+#include <string.h>
+
 namespace sdfb200 {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
@@ -14,8 +16,9 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
 size_t field_tc_packed_bytes(const sdfb200_field_t& f, const FieldPlan& p);
 bool field_tc_supported(const sdfb200_field_t& f, const FieldPlan& p);
 int field_tc_pack(const sdfb200_field_t& f, const FieldPlan& p, char* blob, cudaStream_t st);
+bool field_tc_render_supported(const sdfb200_field_t& f, const FieldPlan& p, int n_samples);
 int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* blob, const void* table, const sdfb200_field_in_t& in,
-                     const sdfb200_field_out_t& out, float* ws, size_t ws_floats, cudaStream_t st);
+                     const sdfb200_field_out_t& out, const TcRender* rnd, float* ws, size_t ws_floats, cudaStream_t st);
 size_t field_tc_workspace_floats(const sdfb200_field_t& f, const FieldPlan& p, int64_t n_points);
 
 static int plan_or_fail(const sdfb200_field_t* f, FieldPlan& p) {
@@ -53,6 +56,7 @@ extern "C" size_t sdfb200_struct_size(int32_t which) {
     case 3: return sizeof(sdfb200_field_in_t);
     case 4: return sizeof(sdfb200_field_out_t);
     case 5: return sizeof(sdfb200_render_out_t);
+    case 6: return sizeof(sdfb200_field_render_t);
     default: return 0;
   }
 }
@@ -109,7 +113,7 @@ extern "C" int sdfb200_field_forward(const sdfb200_field_t* f, const void* packe
   // the rare callers that want it (forward_geonetwork) take the exact-fp32 kernels, which read the same packed blob
   const bool fused = p.tc_bytes > 0;
   if (f->precision != SDFB200_PRECISION_FP32 && fused && out->geo_feature == nullptr)
-    return field_tc_forward(*f, p, (const char*)packed, table, *in, *out, (float*)wsp, ws_floats, (cudaStream_t)stream);
+    return field_tc_forward(*f, p, (const char*)packed, table, *in, *out, nullptr, (float*)wsp, ws_floats, (cudaStream_t)stream);
   // shapes outside the fused family run the generic kernels with tensor-core GEMMs; the fused family's geo-feature requests keep
   // the exact-fp32 engine (unchanged behaviour)
   // numerical gradients divide sdf differences by 2 delta (~1e-3): they need the sdf to fp32 accuracy, which 2^-16-relative GEMMs do not
@@ -119,14 +123,84 @@ extern "C" int sdfb200_field_forward(const sdfb200_field_t* f, const void* packe
   return field_forward_fp32(*f, p, (const char*)packed, table, *in, *out, (float*)wsp, ws_floats, (cudaStream_t)stream, gemm_planes);
 }
 
-// building-block test of the generic tcgen05 Linear (tc_linear.cu) against a reference GEMM: same arguments as the internal sgemm()
-namespace sdfb200 {
-int tc_gemm(int planes, int epi, const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M, int Np, int Kp,
-            const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st);
+// ---------------------------------------------------------------------------------------------------------------------
+// field + compositing in one call.  Fused into the tensor-core kernel when every 128-point tile holds whole rays; otherwise the
+// same result is composed from sdfb200_field_forward + the compositing kernels (per-sample heads staged in the workspace).
+// ---------------------------------------------------------------------------------------------------------------------
+static size_t render_stage_floats(int64_t n_points) { return (size_t)n_points * 9 + 64; }   // alpha|density, rgb(3), normals(3), weights, transmittance
+
+extern "C" size_t sdfb200_field_render_workspace_bytes(const sdfb200_field_t* f, int64_t n_rays, int32_t n_samples) {
+  if (n_rays < 0 || n_samples < 1) return 0;
+  const int64_t n = n_rays * (int64_t)n_samples;
+  const size_t base = sdfb200_field_workspace_bytes(f, n);
+  if (base == 0) return 0;
+  FieldPlan p;
+  if (plan_or_fail(f, p)) return 0;
+  const bool fused = f->precision != SDFB200_PRECISION_FP32 && p.tc_bytes > 0 && field_tc_render_supported(*f, p, n_samples);
+  return base + (fused ? 0 : render_stage_floats(n) * sizeof(float)) + 256;
 }
-extern "C" int sdfb200_debug_tc_linear(int32_t planes, int32_t epi, const float* X, int32_t ldx, const float* W, const float* bias, float* Y,
-                                       int32_t ldy, int64_t M, int32_t Np, int32_t Kp, const float* aux, int32_t ldaux, int32_t aux_cols,
-                                       void* scratch, void* stream) {
-  SDFB_REQUIRE(X && W && Y && scratch && M >= 0, "NULL pointer");
-  return tc_gemm(planes, epi, X, ldx, W, bias, Y, ldy, M, Np, Kp, aux, ldaux, aux_cols, scratch, (cudaStream_t)stream);
+
+extern "C" int sdfb200_field_render(const sdfb200_field_t* f, const void* packed, const void* table, const sdfb200_field_in_t* in,
+                                    const sdfb200_field_out_t* sample_out, const sdfb200_field_render_t* rnd, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  FieldPlan p;
+  int r = plan_or_fail(f, p);
+  if (r) return r;
+  SDFB_REQUIRE(packed && in && rnd, "NULL pointer");
+  SDFB_REQUIRE(in->n_rays >= 0 && in->n_samples >= 1, "bad sizes");
+  if (in->n_rays == 0) return 0;
+  SDFB_REQUIRE(in->origins && in->directions && in->bins, "field_render needs origins, directions and bins");
+  SDFB_REQUIRE(!f->use_grid_feature || table != nullptr, "grid table is NULL");
+  SDFB_REQUIRE(workspace != nullptr, "workspace is NULL");
+  if (rnd->out.rgb) SDFB_REQUIRE(rnd->bg_mode == SDFB200_BG_LAST_SAMPLE || rnd->bg != nullptr, "rgb output needs a background");
+  if (rnd->out.depth) SDFB_REQUIRE(rnd->out.steps_minmax != nullptr, "depth output needs steps_minmax (pre-set to {+inf,-inf})");
+  sdfb200_field_out_t so;
+  if (sample_out) so = *sample_out; else memset(&so, 0, sizeof(so));
+  uintptr_t wsp = ((uintptr_t)workspace + 255) & ~(uintptr_t)255;
+  const size_t lost = wsp - (uintptr_t)workspace;
+  SDFB_REQUIRE(workspace_bytes > lost, "workspace too small");
+  const size_t ws_floats = (workspace_bytes - lost) / sizeof(float);
+  const int64_t N = in->n_rays * (int64_t)in->n_samples;
+  const bool fused = f->precision != SDFB200_PRECISION_FP32 && p.tc_bytes > 0 && so.geo_feature == nullptr &&
+                     field_tc_render_supported(*f, p, in->n_samples);
+  if (fused) {
+    TcRender t;
+    t.enabled = 1; t.from_density = rnd->from_density; t.bg_mode = rnd->bg_mode; t.clamp01 = rnd->clamp01; t.bg = rnd->bg;
+    t.rgb = rnd->out.rgb; t.depth = rnd->out.depth; t.normal = rnd->out.normal; t.accumulation = rnd->out.accumulation;
+    t.bg_transmittance = rnd->bg_transmittance; t.weights = rnd->weights; t.steps_minmax = rnd->out.steps_minmax;
+    r = field_tc_forward(*f, p, (const char*)packed, table, *in, so, &t, (float*)wsp, ws_floats, (cudaStream_t)stream);
+    if (r) return r;
+  } else {
+    const size_t stage = render_stage_floats(N);
+    SDFB_REQUIRE(ws_floats > stage, "workspace too small (use sdfb200_field_render_workspace_bytes)");
+    float* st = (float*)wsp + (ws_floats - stage);
+    float* s_a = st;                 // alpha or density [N]
+    float* s_rgb = s_a + N;          // [N,3]
+    float* s_nrm = s_rgb + 3 * N;    // [N,3]
+    float* s_w = s_nrm + 3 * N;      // [N]
+    if (rnd->from_density) { if (!so.density) so.density = s_a; } else { if (!so.alpha) so.alpha = s_a; }
+    if (!so.rgb) so.rgb = s_rgb;
+    if (!so.normals) so.normals = s_nrm;
+    r = sdfb200_field_forward(f, packed, table, in, &so, (void*)wsp, (ws_floats - stage) * sizeof(float), stream);
+    if (r) return r;
+    float* w = rnd->weights ? rnd->weights : s_w;
+    if (rnd->from_density) {
+      // transmittance[:, -1] (the transmittance BEFORE the last sample) is VolSDF's bg_transmittance (models/volsdf.py:67-68)
+      float* Tbuf = rnd->bg_transmittance ? s_w + N : nullptr;
+      r = sdfb200_weights_from_density(so.density, in->bins, in->n_rays, in->n_samples, w, Tbuf, stream);
+      if (r) return r;
+      if (Tbuf)
+        SDFB_CUDA(cudaMemcpy2DAsync(rnd->bg_transmittance, sizeof(float), Tbuf + (in->n_samples - 1), (size_t)in->n_samples * sizeof(float),
+                                    sizeof(float), (size_t)in->n_rays, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+      r = sdfb200_render(w, so.rgb, so.normals, in->bins, rnd->bg, rnd->bg_mode, rnd->clamp01, 0, in->n_rays, in->n_samples, &rnd->out, stream);
+      if (r) return r;
+    } else {
+      r = sdfb200_render_alphas(so.alpha, so.rgb, so.normals, in->bins, rnd->bg, rnd->bg_mode, rnd->clamp01, in->n_rays, in->n_samples,
+                                rnd->weights, rnd->bg_transmittance, &rnd->out, stream);
+      if (r) return r;
+    }
+  }
+  if (rnd->out.depth && rnd->clip_depth) return sdfb200_depth_clip(rnd->out.depth, rnd->out.steps_minmax, in->n_rays, stream);
+  return 0;
 }
+

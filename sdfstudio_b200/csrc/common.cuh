@@ -65,4 +65,24 @@ __device__ __forceinline__ float dsoftplus100_from_h(float h) { return -expm1f(-
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+// float atomic min / max by compare-and-swap (used for the batch-global steps.min()/max() of DepthRenderer, renderers.py:257)
+__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
+  int* ia = reinterpret_cast<int*>(addr);
+  int old = *ia;
+  while (__int_as_float(old) > v) {
+    const int assumed = old;
+    old = atomicCAS(ia, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
+  int* ia = reinterpret_cast<int*>(addr);
+  int old = *ia;
+  while (__int_as_float(old) < v) {
+    const int assumed = old;
+    old = atomicCAS(ia, assumed, __float_as_int(v));
+    if (old == assumed) break;
+  }
+}
+
 }  // namespace sdfb200

@@ -1,8 +1,13 @@
 // Fused tcgen05 evaluation of the SDF field (SDFB200_PRECISION_BF16X3 / _BF16) for the neus-facto family of shapes:
-// geo MLP in-256-256-(1+256), colour MLP cin-256-256-3, analytic d sdf/dx, 2-feature hash grid (fp32 or fp16 table).
+// geo MLP in-256-256-(1+256), colour MLP cin-256-256-3, analytic d sdf/dx, 2-feature hash grid (fp32 or fp16 table),
+// optionally followed IN THE SAME KERNEL by the per-ray compositing (alpha / density -> transmittance -> weights -> rgb, depth,
+// normal, accumulation: cameras/rays.py:131-230, model_components/renderers.py:53-118,171-261,284-295).
 //
-// One persistent CTA per SM walks 128-point tiles.  Per tile (everything stays on chip except two L2-resident spills):
-//   encode   16 epilogue warps: position, contraction, PE, hash gathers (+ jacobian) -> bf16 split planes in smem
+// Persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2): every CTA walks its own 128-point tiles, one MMA covers the two
+// tiles of a pair (M = 256) and each CTA streams only HALF of every weight tile (rows [0,N/2) / [N/2,N) of the B operand).
+// Per tile (everything stays on chip except three L2-resident spills):
+//   encode   4 gather warps (one thread per point), decoupled from the compute warps and one tile ahead: position,
+//            contraction, hash gathers (+ jacobian), PE -> bf16 split planes in smem (double buffered)
 //   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), next layer's A operand written to TMEM
 //   sdf      fp32 dot of h2 with row 0 of W2 on CUDA cores (exact fp32: the SDF drives NeuS alpha / Laplace density)
 //   (no G2)  the geo feature is linear in h2, so colour layer 0 is pre-multiplied at pack time: Wc = Wgf W2', and h2 itself
@@ -10,51 +15,52 @@
 //   B1 B0    reverse sweep: g2 = W2[0,:]*sp'(z2), g1 = (W1^T g2)*sp'(z1), gin = W0^T g1;  sp'(z1) spilled at G0
 //   grad     d sdf/dx = gin_x + PE jacobian + grid jacobian / 4      (what autograd computes at sdf_field.py:647-654)
 //   C0 C1    relu MLP on [x, dir-enc, grad, geo feature, appearance]; last 256->3 layer as fp32 dots; sigmoid + padding
-//   heads    Laplace density, NeuS alpha, occupancy, normals
-// MMA = tcgen05.mma kind::f16 (bf16 x bf16 -> fp32), M=128.  bf16x3: a0*w0 + a1*w0 + a0*w1 with a = a0+a1, w = w0+w1
-// (error ~2^-16 relative, fp32 accumulate).  Weights stream through a 3-stage shared-memory ring filled by 1-D bulk
-// copies (UBLKCP) from a pre-packed image.  Warp roles: 0-15 epilogues, 16 weight producer, 17 MMA issuer.  The epilogue
-// warps encode the NEXT tile's input in seven slices, one before each wait for an MMA phase, into a double-buffered
-// smem operand -- the L2-latency-bound hash gathers run in the shadow of the tensor-core work.
+//   heads    Laplace density, NeuS alpha, occupancy, normals; optional per-sample outputs
+//   render   (fused mode) segmented prefix product over the rays of the tile in double, weights, per-ray sums
+// MMA = tcgen05.mma kind::f16 (bf16 x bf16 -> fp32).  bf16x3: a0*w0 + a1*w0 + a0*w1 with a = a0+a1, w = w0+w1
+// (error ~2^-16 relative, fp32 accumulate).  Weights stream through a shared-memory ring filled by 1-D bulk copies (UBLKCP)
+// from a pre-packed image.  Warp roles: 0-7 epilogues (2 threads per row: 128 columns each), 8-11 gather/encode,
+// 12 weight producer, 13 MMA issuer (leader CTA) / weight-arrival relay (peer CTA).
 #include "field_plan.h"
 #include "grid.cuh"
 #include "tc_common.cuh"
 
-#include <stdlib.h>
-
 namespace sdfb200 {
 using namespace tc;
 
-constexpr int kTcThreads = 576;   // 16 epilogue warps + weight producer + MMA issuer
-constexpr int kEpiThreads = 512;
-constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kGatherWarps = 4;
+constexpr int kWarpProducer = kEpiWarps + kGatherWarps;      // 12
+constexpr int kWarpMma = kWarpProducer + 1;                  // 13
+constexpr int kTcThreads = (kWarpMma + 1) * 32;              // 448
+constexpr int kStages = 6;
 constexpr int kKB = 32;           // K per streamed weight block
 constexpr int kMaxGridDim = 32;
-constexpr int kMaxPe = 64;         // PE columns (2 * 3 * degree)
+constexpr int kMaxPe = 60;        // PE columns (2 * 3 * degree), degree <= 10
+constexpr int kPeRows = 64;       // rows reserved for the PE jacobian in the scratch
 constexpr int kInK = 96;          // padded K of the two small-K operands (geo input, colour misc input)
 constexpr float kHalfPiF = 1.5707963267948966f;
-// per-CTA scratch: softplus'(z1) unorm16 [64 KB] | h2 planes [P x 64 KB] | 2 x input jacobian
-// encoder side buffer: input jacobian (PE derivative [64][128] f32 | grid [96][128] f32) | static colour operand [P][11][128][16 B]
-constexpr size_t kJRBytes = (size_t)(kMaxPe + kMaxGridDim * 3) * 128 * 4;   // input jacobian: PE [64][128] f32 | grid [32*3][128] f32
-__host__ __device__ constexpr size_t kEncBufBytes(int planes) { return kJRBytes; }
-__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 65536 + (size_t)planes * 65536 + 2 * kEncBufBytes(planes); }
+// kernel order of the geo input columns (K = 96): [grid features 0..31 | PE | x(3) | zero padding] -- every group of four hash
+// levels is one aligned 16-byte operand chunk.  W0 (columns) and W0^T (rows) are permuted accordingly at pack time.
+// per-CTA scratch: softplus'(z1) unorm16 [64 KB] | h2 planes [P x 64 KB] | 2 x input jacobian (PE [64][128] f32 | grid [96][128] f32)
+constexpr size_t kJRBytes = (size_t)(kPeRows + kMaxGridDim * 3) * 128 * 4;
+__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 65536 + (size_t)planes * 65536 + 2 * kJRBytes; }
 
 enum { L_G0 = 0, L_G1, L_B1, L_B0, L_C0H, L_C0MISC, L_C1, L_COUNT };
 
 struct TcLayer {
   unsigned long long w_off;  // byte offset of the packed planes inside the blob
-  int Np;                    // rows of the weight tile (UMMA N)
+  int Np;                    // rows of the weight tile (UMMA N); each CTA of a pair holds Np / 2 of them
   int nkb;                   // K blocks of 32
 };
 
 struct TcArgs {
   sdfb200_grid_t grid;
   TcLayer layer[L_COUNT];
-  int use_grid, pe_degree, use_pe, contraction, in_dim, pe_dim, grid_dim, cm_dim, app_dim, use_n_dot_v;
+  int use_grid, pe_degree, use_pe, contraction, in_dim, pe_dim, grid_dim, app_dim, use_n_dot_v;
   int mode;  // 0: sdf only (G0, G1)   1: everything
-  int timing;
-  int pol_table, pol_scratch;   // L2 policies: 0 normal, 1 evict_first, 2 evict_last
-  int n_samples, has_bins, n_tiles;
+  int n_samples, has_bins, n_tiles, n_tile_pairs;
   long long n_points;
   float rgb_padding, cos_anneal;
   const float *origins, *directions, *bins, *appearance, *variance, *beta, *beta_min;
@@ -65,35 +71,32 @@ struct TcArgs {
   char* scratch;
   unsigned long long scratch_per_cta;
   sdfb200_field_out_t out;
+  TcRender rnd;
 };
 
-// pack fp32 W (row n, column k at W[n*ldw + colmap(k)]) into bf16 split planes, K-blocked canonical layout
-struct ColMap { short src[kInK]; };   // packed K index -> source column of the fp32 weight (-1 = zero); identity when unused
-__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int planes, int use_map, const ColMap map,
-                          __nv_bfloat16* __restrict__ out) {
+// pack fp32 W (row n, column k at W[rowmap(n)*ldw + colmap(k)]) into bf16 split planes: K-blocked, N split in two halves (one per
+// CTA of a pair), canonical K-major no-swizzle layout inside a half:  [K-block][half][plane][k/8][row in half][8 bf16]
+struct IdxMap { short src[kInK]; };   // packed index -> source index (-1 = zero); identity when unused
+__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int planes, int use_colmap, const IdxMap colmap,
+                          int use_rowmap, const IdxMap rowmap, __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nblocks * Np * kKB) return;
   const int kk = idx % kKB;
   const int n = (idx / kKB) % Np;
   const int b = idx / (kKB * Np);
   const int k = b * kKB + kk;
-  const int src = use_map ? (k < kInK ? map.src[k] : -1) : k;
-  const float w = (n < N && k < K && src >= 0) ? W[(size_t)n * ldw + src] : 0.f;
+  const int ks = use_colmap ? (k < kInK ? colmap.src[k] : -1) : (k < K ? k : -1);
+  const int ns = use_rowmap ? (n < kInK ? rowmap.src[n] : -1) : (n < N ? n : -1);
+  const float w = (ns >= 0 && ks >= 0) ? W[(size_t)ns * ldw + ks] : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
-  const size_t plane_elems = (size_t)Np * kKB;
-  const size_t base = (size_t)b * planes * plane_elems;
-  const size_t off = (size_t)(kk / 8) * (Np * 8) + (size_t)n * 8 + (kk % 8);
+  const int nh = Np / 2, half = n / nh, nl = n - half * nh;
+  const size_t plane_elems = (size_t)nh * kKB;
+  const size_t base = ((size_t)b * 2 + half) * planes * plane_elems;
+  const size_t off = (size_t)(kk / 8) * (nh * 8) + (size_t)nl * 8 + (kk % 8);
   out[base + off] = hi;
   if (planes > 1) out[base + plane_elems + off] = lo;
 }
-
-// debug: per-phase clock64 stamps of CTA 0's first tiles (SDFB200_TC_TIMING=1), read by sdfb200_debug_tc_timing
-__device__ long long g_tc_timing[16 * 32];
-#define TC_STAMP(k)                                                                       \
-  do {                                                                                    \
-    if (a.timing && blockIdx.x == 0 && tid == 0 && tile_no < 16) g_tc_timing[tile_no * 32 + (k)] = clock64(); \
-  } while (0)
 
 __device__ __forceinline__ uint64_t l2_policy(int kind) {
   return kind == 1 ? l2_policy_evict_first() : (kind == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
@@ -131,36 +134,22 @@ __device__ __forceinline__ void softplus100_fast(float z, float& h, float& dsig)
   h = lin ? z : fast_lg2(u) * 0.006931471805599453f;
   dsig = lin ? 1.0f : e * fast_rcp(u);
 }
-__device__ __forceinline__ float softplus100_fast_h(float z) {
-  const float e = fast_ex2(fminf(z, 0.3f) * 144.26950408889634f);
-  return z > 0.2f ? z : fast_lg2(1.0f + e) * 0.006931471805599453f;
-}
-// softplus'(z) recovered from h = softplus(z):  1 - exp(-100 h)
-__device__ __forceinline__ float dsoftplus_from_h_fast(float h) { return 1.0f - fast_ex2(h * -144.26950408889634f); }
 
-__device__ __forceinline__ void named_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-// store one bf16 element (split into P planes) of the small-K smem operand: layout [plane][k/8][row][8]
-template <int P>
-__device__ __forceinline__ void store_in(uint8_t* inA, int row, int col, float v) {
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  const uint32_t off = (uint32_t)(col >> 3) * 2048u + (uint32_t)row * 16u + (uint32_t)(col & 7) * 2u;
-  *reinterpret_cast<__nv_bfloat16*>(inA + off) = hi;
-  if (P > 1) *reinterpret_cast<__nv_bfloat16*>(inA + (kInK / 8) * 2048 + off) = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
-
 // sample position of point p (ray r, sample s): o + d * t_start, then SceneContraction (cameras/rays.py:61-73,
-// spatial_distortions.py:66-73).  Also returns the ray direction and the bin width.
-struct PointGeom { float px, py, pz, dx, dy, dz, delta; long long ray; };
+// spatial_distortions.py:66-73).  Also returns the ray direction, the bin start and the bin width.
+struct PointGeom { float px, py, pz, dx, dy, dz, delta, t0, t1; long long ray; };
 __device__ __forceinline__ PointGeom point_geom(const TcArgs& a, long long p) {
   PointGeom g;
-  g.dx = g.dy = g.dz = 0.f; g.delta = 0.f;
+  g.dx = g.dy = g.dz = 0.f; g.delta = 0.f; g.t0 = g.t1 = 0.f;
   g.ray = a.has_bins ? p / a.n_samples : p;
   if (a.has_bins) {
     const int smp = (int)(p - g.ray * a.n_samples);
     const float t0 = __ldg(a.bins + g.ray * (a.n_samples + 1) + smp);
-    g.delta = __fsub_rn(__ldg(a.bins + g.ray * (a.n_samples + 1) + smp + 1), t0);
+    g.t0 = t0;
+    g.t1 = __ldg(a.bins + g.ray * (a.n_samples + 1) + smp + 1);
+    g.delta = __fsub_rn(g.t1, t0);
     g.dx = __ldg(a.directions + g.ray * 3); g.dy = __ldg(a.directions + g.ray * 3 + 1); g.dz = __ldg(a.directions + g.ray * 3 + 2);
     g.px = __fadd_rn(__ldg(a.origins + g.ray * 3 + 0), __fmul_rn(g.dx, t0));
     g.py = __fadd_rn(__ldg(a.origins + g.ray * 3 + 1), __fmul_rn(g.dy, t0));
@@ -181,116 +170,148 @@ __device__ __forceinline__ PointGeom point_geom(const TcArgs& a, long long p) {
   return g;
 }
 
-// One slice of the NEXT tile's input encoding, executed by the 16 epilogue warps right before they wait for an MMA phase
-// (so the L2-latency-bound gathers run in the shadow of the tensor-core work).  Thread (row, q) owns levels q, q+4, ..
-//   slices 0-3: one hash level each (8 gathers, blend, jacobian)            slice 4: positional encoding (+ derivative)
-//   slice 5   : static colour-operand columns (x, dir-enc, appearance)      slice 6: x columns, zero padding, fences
-// Outputs: geo input operand (bf16 planes, smem, canonical layout) and, in the per-CTA global scratch, the per-point
-// input jacobian JR[c][3] (d input_c / d x, laid out so that EB0 reads its 24 columns as 18 coalesced float4) and the
-// static colour columns already in operand layout (staged into smem later by one bulk copy per plane).
+// one 16-byte chunk (8 consecutive K columns of one row) of a small-K smem operand, all planes: layout [plane][k/8][row][8]
 template <int P>
-__device__ __forceinline__ void encode_slice(const TcArgs& a, int tile, int slice, int row, int q, uint8_t* inA, uint8_t* enc) {
-  if (tile >= a.n_tiles) return;
-  float* Jpe = reinterpret_cast<float*>(enc);                       // [pe column][row]     d PE_i / d x_axis(i)
-  float* Jg = Jpe + kMaxPe * 128;                                    // [grid col * 3 + d][row]
+__device__ __forceinline__ void store_chunk(uint8_t* inA, int row, int chunk, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+  *reinterpret_cast<uint4*>(inA + (size_t)chunk * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + (size_t)chunk * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// Geo input of one tile, one thread per point (gather warps): hash levels in groups of four (= one operand chunk), PE, x.
+// Outputs: the smem operand (bf16 planes, kernel column order) and, in the per-CTA global scratch, the per-point input
+// jacobian: PE [i][row] (d PE_i / d x_axis(i)) and grid [(col*3 + d)][row] (with the 1/4 of (x+2)/4 folded in).
+template <int P>
+__device__ __forceinline__ void encode_tile(const TcArgs& a, int tile, int row, uint8_t* inA, uint8_t* enc, uint64_t pol_table) {
+  float* Jpe = reinterpret_cast<float*>(enc);
+  float* Jg = Jpe + kPeRows * 128;
   const long long p_raw = (long long)tile * 128 + row;
   const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
   const PointGeom g = point_geom(a, p);
-  const uint64_t pol_stream = l2_policy_evict_normal();   // jacobian / colour columns live for a whole tile: keep them in L2
-  if (slice < 4) {
-    const int l = q + 4 * slice;
-    if (l < a.grid.n_levels && a.grid_dim > 0) {
+  const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;   // sdf_field.py:384
+  // ---- hash grid: chunks 0..3 ----
+#pragma unroll 1
+  for (int ch = 0; ch < 4; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = ch * 4 + j;
       float o[2] = {0.f, 0.f};
       float dj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      if (a.use_grid && l < a.grid.active_levels) {
-        const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;
-        if (a.grid.table_dtype == SDFB200_DT_F16) encode_level<__half, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
-        else encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, l2_policy(a.pol_table));
+      if (a.use_grid && l < a.grid.n_levels && l < a.grid.active_levels) {
+        if (a.grid.table_dtype == SDFB200_DT_F16) encode_level<__half, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, pol_table);
+        else encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, pol_table);
       }
+      v[2 * j] = o[0]; v[2 * j + 1] = o[1];
+      if (a.mode != 0 && l < a.grid.n_levels) {
 #pragma unroll
-      for (int f = 0; f < 2; ++f) {
-        const int cg = l * 2 + f;
-        store_in<P>(inA, row, 3 + a.pe_dim + cg, o[f]);
-        // positions = (x + 2) / 4 (sdf_field.py:384): the 1/4 is folded into the stored jacobian
-        st_stream(Jg + (cg * 3 + 0) * 128 + row, 0.25f * dj[f][0], pol_stream);
-        st_stream(Jg + (cg * 3 + 1) * 128 + row, 0.25f * dj[f][1], pol_stream);
-        st_stream(Jg + (cg * 3 + 2) * 128 + row, 0.25f * dj[f][2], pol_stream);
-      }
-    }
-  } else if (slice == 4) {
-    const int deg = a.pe_degree, half = 3 * deg;
-    const float pc[3] = {g.px, g.py, g.pz};
-    for (int i = q; i < half; i += 4) {                   // PE: sin(x 2^k) | sin(x 2^k + pi/2)   (encodings.py:194-198)
-      const int b = i / deg, k = i - b * deg;
-      const float fr = (float)(1 << k);
-      const float sarg = pc[b] * fr;
-      float s0, c0, s1, c1;
-      sincosf(sarg, &s0, &c0);
-      sincosf(sarg + kHalfPiF, &s1, &c1);
-      store_in<P>(inA, row, 3 + i, a.use_pe ? s0 : 0.f);
-      store_in<P>(inA, row, 3 + half + i, a.use_pe ? s1 : 0.f);
-      // autograd of sin on the forward's own fp32 arguments: d/dx_b = 2^k cos(arg)
-      st_stream(Jpe + i * 128 + row, a.use_pe ? fr * c0 : 0.f, pol_stream);
-      st_stream(Jpe + (half + i) * 128 + row, a.use_pe ? fr * c1 : 0.f, pol_stream);
-    }
-  } else if (slice == 5) {
-    if (a.mode != 0) {
-      // static colour columns (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(27) | appearance | 0, for the CURRENT
-      // tile: `inA` is that tile's own operand buffer, whose geo input G0 has already consumed
-      const float pc[3] = {g.px, g.py, g.pz};
-      const float dd[3] = {g.dx, g.dy, g.dz};
-      for (int ch = q; ch < 11; ch += 4) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) {
-          float v2[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int j = ch * 8 + e2 * 2 + u;
-            float val = 0.f;
-            if (j < 3) val = pc[j];
-            else if (j < 15) { const int i = j - 3; val = sinf(dd[i >> 2] * (float)(1 << (i & 3))); }
-            else if (j < 27) { const int i = j - 15; val = sinf(dd[i >> 2] * (float)(1 << (i & 3)) + kHalfPiF); }
-            else if (j < 30) val = dd[j - 27];
-            else if (j < 30 + a.app_dim) val = a.appearance ? __ldg(a.appearance + g.ray * a.app_dim + (j - 30)) : 0.f;
-            v2[u] = val;
-          }
-          split2(v2[0], v2[1], hi[e2], lo[e2]);
+        for (int f = 0; f < 2; ++f) {
+          const int cg = l * 2 + f;
+          Jg[(cg * 3 + 0) * 128 + row] = 0.25f * dj[f][0];
+          Jg[(cg * 3 + 1) * 128 + row] = 0.25f * dj[f][1];
+          Jg[(cg * 3 + 2) * 128 + row] = 0.25f * dj[f][2];
         }
-        *reinterpret_cast<uint4*>(inA + (size_t)(1 + ch) * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + (size_t)(1 + ch) * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
       }
     }
-  } else {
-    if (q == 0) {
-      store_in<P>(inA, row, 0, g.px); store_in<P>(inA, row, 1, g.py); store_in<P>(inA, row, 2, g.pz);
-    } else if (q == 1) {
-      for (int c = a.in_dim; c < kInK; ++c) store_in<P>(inA, row, c, 0.f);
+    store_chunk<P>(inA, row, ch, v);
+  }
+  // ---- PE | x | zero padding: chunks 4..11.  Kernel column 32 + i holds PE_i, 32 + pe_dim + j holds x_j ----
+  const int deg = a.pe_degree, half = 3 * deg;
+  const float pc[3] = {g.px, g.py, g.pz};
+#pragma unroll 1
+  for (int ch = 4; ch < kInK / 8; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int i = ch * 8 + e - 32;
+      float val = 0.f;
+      if (i < a.pe_dim) {                                   // sin(x 2^k) | sin(x 2^k + pi/2)   (encodings.py:194-198)
+        const int ia = i >= half ? i - half : i;
+        const int b = ia / deg, k = ia - b * deg;
+        const float fr = (float)(1 << k);
+        const float arg = i >= half ? pc[b] * fr + kHalfPiF : pc[b] * fr;
+        float s, c;
+        sincosf(arg, &s, &c);
+        val = a.use_pe ? s : 0.f;
+        // autograd of sin on the forward's own fp32 arguments: d/dx_b = 2^k cos(arg)
+        if (a.mode != 0) Jpe[i * 128 + row] = a.use_pe ? fr * c : 0.f;
+      } else if (i < a.pe_dim + 3) {
+        val = pc[i - a.pe_dim];
+      }
+      v[e] = val;
     }
-    fence_async_smem();                                        // smem operand -> async proxy (UMMA reads it)
+    store_chunk<P>(inA, row, ch, v);
   }
 }
 
+// static colour-operand columns of a tile (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(24) | dir(3) | appearance | 0,
+// written IN PLACE over the tile's geo input once G0 has consumed it (chunk 0 = [grad, n.v] comes from the epilogue warps)
 template <int P>
-__global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constant__ TcArgs a) {
+__device__ __forceinline__ void colour_static_tile(const TcArgs& a, int tile, int row, uint8_t* inA) {
+  const long long p_raw = (long long)tile * 128 + row;
+  const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
+  const PointGeom g = point_geom(a, p);
+  const float pc[3] = {g.px, g.py, g.pz};
+  const float dd[3] = {g.dx, g.dy, g.dz};
+#pragma unroll 1
+  for (int ch = 0; ch < 11; ++ch) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int j = ch * 8 + e;
+      float val = 0.f;
+      if (j < 3) val = pc[j];
+      else if (j < 15) { const int i = j - 3; val = sinf(dd[i >> 2] * (float)(1 << (i & 3))); }
+      else if (j < 27) { const int i = j - 15; val = sinf(dd[i >> 2] * (float)(1 << (i & 3)) + kHalfPiF); }
+      else if (j < 30) val = dd[j - 27];
+      else if (j < 30 + a.app_dim) val = a.appearance ? __ldg(a.appearance + g.ray * a.app_dim + (j - 30)) : 0.f;
+      v[e] = val;
+    }
+    store_chunk<P>(inA, row, 1 + ch, v);
+  }
+}
+
+#ifdef SDFB200_TC_TIMING
+__device__ long long g_tc_timing[16 * 32];
+#define TC_STAMP(k)                                                                                                  \
+  do {                                                                                                               \
+    if (blockIdx.x == 0 && tid == 0 && tile_no < 16) g_tc_timing[tile_no * 32 + (k)] = clock64();                   \
+  } while (0)
+#else
+#define TC_STAMP(k) do { } while (0)
+#endif
+
+template <int P>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   constexpr uint32_t kInBytes = (uint32_t)P * (kInK / 8) * 2048;       // small-K operand (all planes), double buffered
-  constexpr uint32_t kStageBytes = (uint32_t)P * 256 * kKB * 2;        // one weight K-block, all planes
+  constexpr uint32_t kStageBytes = (uint32_t)P * 128 * kKB * 2;        // this CTA's half of one weight K-block, all planes
   uint8_t* inA0 = smem;
   uint8_t* ring = smem + 2 * kInBytes;
   float* fbuf = reinterpret_cast<float*>(ring + kStages * kStageBytes);
-  float* red = fbuf;                  // [3][4][128] partial sums
-  float* prm = fbuf + 12 * 128;       // [9][256] biases / fp32 weight rows used by the epilogues
-  __shared__ uint64_t full[kStages], empty[kStages], dfull;
+  float* red = fbuf;                  // [3][2][128] partial sums
+  float* prm = fbuf + 6 * 128;        // [9][256] biases / fp32 weight rows used by the epilogues
+  float* racc = prm + 9 * 256;        // [8][4] per-ray accumulators of the fused compositing (rays spanning several warps)
+  float* lastrgb = racc + 32;         // [4][3]
+  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_ready, in_ready, misc_ready;
+  __shared__ double wtot[4];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&peer_full[s], 1); }
     mbar_init(&dfull, 1);
+    mbar_init(&g0done, 1);
+    mbar_init(&a_ready, 2 * kEpiWarps);
+    mbar_init(&in_ready, 2 * kGatherWarps);
+    mbar_init(&misc_ready, 2 * kGatherWarps);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (warp == 0) tmem_alloc2<512>(&tmem_base_s);
   {
     const char* blob = a.blob;
     const float* src[9] = {reinterpret_cast<const float*>(blob + a.b_g0), reinterpret_cast<const float*>(blob + a.b_g1),
@@ -299,55 +320,76 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
                            reinterpret_cast<const float*>(blob + a.w_c2), reinterpret_cast<const float*>(blob + a.w_c2) + 256,
                            reinterpret_cast<const float*>(blob + a.w_c2) + 512};
     for (int i = tid; i < 9 * 256; i += kTcThreads) prm[i] = src[i >> 8][i & 255];
+    if (tid < 44) racc[tid] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   const uint32_t d_tmem = tmem;          // accumulator: columns [0,256)
   const uint32_t a_tmem = tmem + 256;    // A planes: plane p at columns 256 + 128 p
   const int nphase_layers = a.mode == 0 ? 2 : L_COUNT;
+  // leader-side barriers that both CTAs arrive on
+  const uint32_t a_ready_r = mapa_shared(smem_u32(&a_ready), 0);
+  const uint32_t in_ready_r = mapa_shared(smem_u32(&in_ready), 0);
+  const uint32_t misc_ready_r = mapa_shared(smem_u32(&misc_ready), 0);
 
-  if (warp == 16) {
-    // ============================== weight producer ==============================
+  if (warp == kWarpProducer) {
+    // ============================== weight producer (this CTA's half of every weight tile) ==============================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
         for (int L = 0; L < nphase_layers; ++L) {
           const TcLayer ly = a.layer[L];
-          const uint32_t bytes = (uint32_t)P * ly.Np * kKB * 2;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.blob) + ly.w_off;
+          const uint32_t bytes = (uint32_t)P * (ly.Np / 2) * kKB * 2;
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.blob) + ly.w_off + (size_t)rank * bytes;
           for (int kb = 0; kb < ly.nkb; ++kb, ++it) {
             const int s = it % kStages;
             mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
             mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(ring + (size_t)s * kStageBytes, src + (size_t)kb * bytes, bytes, &full[s]);
+            bulk_g2s(ring + (size_t)s * kStageBytes, src + (size_t)kb * 2 * bytes, bytes, &full[s]);
           }
         }
       }
     }
-  } else if (warp == 17) {
-    // ============================== MMA issuer ==============================
-    uint32_t it = 0;
-    int tile_no = -1;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      ++tile_no;
-      const uint32_t in_base = smem_u32(inA0 + (tile_no & 1) * kInBytes);
-      for (int L = 0; L < nphase_layers; ++L) {
-        const bool continues = (L == L_C0MISC);           // accumulates onto C0GF, no barrier in between
-        if (!continues) {
-          named_sync(1, kEpiThreads + 32);                // "A operand ready" from the epilogue warps
+  } else if (warp == kWarpMma) {
+    if (rank != 0) {
+      // ============================== peer CTA: forward "my half of stage s has landed" to the leader ==============================
+      if (lane == 0) {
+        uint32_t it = 0;
+        for (int tp = pair; tp < a.n_tile_pairs; tp += npairs)
+          for (int L = 0; L < nphase_layers; ++L)
+            for (int kb = 0; kb < a.layer[L].nkb; ++kb, ++it) {
+              const int s = it % kStages;
+              mbar_wait(&full[s], (it / kStages) & 1);
+              mbar_arrive_remote(mapa_shared(smem_u32(&peer_full[s]), 0));
+            }
+      }
+    } else if (lane == 0) {
+      // ============================== MMA issuer (leader CTA, one thread) ==============================
+      uint32_t it = 0, par_a = 0, par_in = 0, par_misc = 0;
+      int tile_no = -1;
+      for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
+        ++tile_no;
+        const uint32_t in_base = smem_u32(inA0 + (tile_no & 1) * kInBytes);
+        for (int L = 0; L < nphase_layers; ++L) {
+          if (L == L_C0MISC) {                                   // accumulates onto C0H; its static columns come from the gather warps
+            mbar_wait_cluster(&misc_ready, par_misc); par_misc ^= 1;
+          } else {
+            mbar_wait_cluster(&a_ready, par_a); par_a ^= 1;     // both CTAs: A operand of this layer staged, D drained
+            if (L == L_G0) { mbar_wait_cluster(&in_ready, par_in); par_in ^= 1; }
+          }
           tc_fence_after();
-        }
-        if (lane == 0) {
           const TcLayer ly = a.layer[L];
           const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
-          const uint32_t idesc = make_idesc_bf16(128, ly.Np);
-          const uint32_t lbo_b = (uint32_t)ly.Np * 16, plane_b = (uint32_t)ly.Np * kKB * 2;
-          uint32_t acc = continues ? 1u : 0u;
+          const uint32_t idesc = make_idesc_bf16(256, ly.Np);
+          const uint32_t lbo_b = (uint32_t)(ly.Np / 2) * 16, plane_b = (uint32_t)(ly.Np / 2) * kKB * 2;
+          uint32_t acc = (L == L_C0MISC) ? 1u : 0u;
           for (int kb = 0; kb < ly.nkb; ++kb, ++it) {
             const int s = it % kStages;
             mbar_wait(&full[s], (it / kStages) & 1);
+            mbar_wait_cluster(&peer_full[s], (it / kStages) & 1);
             tc_fence_after();
             const uint32_t wbase = smem_u32(ring + (size_t)s * kStageBytes);
 #pragma unroll
@@ -357,34 +399,68 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
               const uint64_t b1 = make_smem_desc(wbase + plane_b + j * 2 * lbo_b, lbo_b, 128);
               if (a_in_smem) {
                 const uint64_t a0 = make_smem_desc(in_base + kstep * 2 * 2048, 2048, 128);
-                mma_ss(d_tmem, a0, b0, idesc, acc);
+                mma_ss2(d_tmem, a0, b0, idesc, acc);
                 acc = 1;
                 if (P > 1) {
                   const uint64_t a1 = make_smem_desc(in_base + (kInK / 8) * 2048 + kstep * 2 * 2048, 2048, 128);
-                  mma_ss(d_tmem, a1, b0, idesc, 1);
-                  mma_ss(d_tmem, a0, b1, idesc, 1);
+                  mma_ss2(d_tmem, a1, b0, idesc, 1);
+                  mma_ss2(d_tmem, a0, b1, idesc, 1);
                 }
               } else {
-                mma_ts(d_tmem, a_tmem + kstep * 8, b0, idesc, acc);
+                mma_ts2(d_tmem, a_tmem + kstep * 8, b0, idesc, acc);
                 acc = 1;
                 if (P > 1) {
-                  mma_ts(d_tmem, a_tmem + 128 + kstep * 8, b0, idesc, 1);
-                  mma_ts(d_tmem, a_tmem + kstep * 8, b1, idesc, 1);
+                  mma_ts2(d_tmem, a_tmem + 128 + kstep * 8, b0, idesc, 1);
+                  mma_ts2(d_tmem, a_tmem + kstep * 8, b1, idesc, 1);
                 }
               }
             }
-            mma_commit(&empty[s]);
+            mma_commit2(&empty[s]);
           }
-          if (L != L_C0H) mma_commit(&dfull);             // C0H is completed by C0MISC
+          if (L == L_G0) mma_commit2(&g0done);               // the geo input of this tile has been consumed (gather warps)
+          if (L != L_C0H) mma_commit2(&dfull);               // C0H is completed by C0MISC
         }
+      }
+    }
+  } else if (warp >= kEpiWarps) {
+    // ============================== gather / encode warps: one thread per point, one tile ahead ==============================
+    const int row = (warp - kEpiWarps) * 32 + lane;
+    uint8_t* enc_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta) + 65536 + (size_t)P * 65536;
+    const uint64_t pol_table = l2_policy_evict_last();
+    int tile_no = -1;
+    {
+      const int tile0 = 2 * pair + (int)rank;
+      encode_tile<P>(a, tile0, row, inA0, enc_s, pol_table);
+      fence_async_smem();
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(in_ready_r);
+    }
+    for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
+      ++tile_no;
+      const int tile = 2 * tp + (int)rank;
+      const int buf = tile_no & 1;
+      mbar_wait_backoff(&g0done, tile_no & 1);              // G0 of this tile is complete (hence every MMA of the previous tile)
+      if (a.mode != 0) {
+        colour_static_tile<P>(a, tile, row, inA0 + buf * kInBytes);
+        fence_async_smem();
         __syncwarp();
+        if (lane == 0) mbar_arrive_remote(misc_ready_r);
+      }
+      if (tp + npairs < a.n_tile_pairs) {
+        encode_tile<P>(a, tile + 2 * npairs, row, inA0 + (buf ^ 1) * kInBytes, enc_s + (size_t)(buf ^ 1) * kJRBytes, pol_table);
+        fence_async_smem();
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(in_ready_r);
       }
     }
   } else {
-    // ============================== epilogues + sliced encode of the next tile (16 warps) ==============================
-    const int row = (warp & 3) * 32 + lane;               // tile row == TMEM lane
-    const int q = warp >> 2;                              // column quarter
-    const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+    // ============================== epilogue warps (8): thread (row, q) owns accumulator columns [128 q, 128 q + 128) ==============================
+    const int wq = warp & 3;                              // TMEM lane quadrant
+    const int row = wq * 32 + lane;                       // tile row == TMEM lane
+    const int q = warp >> 2;                              // column half
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     const char* blob = a.blob;
     const float* p_bg0 = prm;             // smem copies (broadcast LDS.128 instead of one LDG per element)
     const float* p_bg1 = prm + 256;
@@ -394,26 +470,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
     const float* p_wc2 = prm + 1536;      // [3][256]
     const float sdf_bias = __ldg(reinterpret_cast<const float*>(blob + a.b_g2));
     const float* b_c2 = reinterpret_cast<const float*>(blob + a.b_c2);
-    float* sig_s = reinterpret_cast<float*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);        // [64 units][128 rows][4]
-    uint8_t* gf_s = reinterpret_cast<uint8_t*>(sig_s) + 65536;                                          // [P][32 units][128][16 B]
-    uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x encoder side buffers
+    uint8_t* sig_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);   // [32 units][128 rows][16 B]
+    uint8_t* gf_s = sig_s + 65536;                                                                      // [P][32 units][128][16 B]
+    uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x input jacobian
     uint32_t dpar = 0;
-    const uint64_t pol_stream = l2_policy(a.pol_scratch);
-
-    // prologue: encode the first tile completely
-    for (int sl = 0; sl < 7; ++sl)
-      if (sl != 5) encode_slice<P>(a, blockIdx.x, sl, row, q, inA0, enc_s);
+    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_keep = l2_policy_evict_normal();
+    auto epi_arrive = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(a_ready_r);
+    };
 
     int tile_no = -1;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
       ++tile_no;
+      const int tile = 2 * tp + (int)rank;
       TC_STAMP(0);
       const int buf = tile_no & 1;
       uint8_t* inA = inA0 + buf * kInBytes;               // geo input now, colour operand later
-      uint8_t* inA_next = inA0 + (buf ^ 1) * kInBytes;
-      uint8_t* enc_cur = enc_s + (size_t)buf * kEncBufBytes(P);
-      uint8_t* enc_next = enc_s + (size_t)(buf ^ 1) * kEncBufBytes(P);
-      const int next_tile = tile + gridDim.x;
+      const uint8_t* enc_cur = enc_s + (size_t)buf * kJRBytes;
       const long long p_raw = (long long)tile * 128 + row;
       const bool valid = p_raw < a.n_points;
       const long long p = valid ? p_raw : a.n_points - 1;
@@ -423,18 +499,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         if (a.out.points_norm) a.out.points_norm[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
         if (a.out.points) { a.out.points[p * 3] = px; a.out.points[p * 3 + 1] = py; a.out.points[p * 3 + 2] = pz; }
       }
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);                  // input operand staged (previous tile / prologue), D and A planes free
+      epi_arrive();                                        // D and the A planes are free (previous tile fully drained)
       TC_STAMP(1);
-      encode_slice<P>(a, next_tile, 0, row, q, inA_next, enc_next);
-      if (a.mode == 0) { encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 2, row, q, inA_next, enc_next); }
 
       // ---------------- E0: h1 = softplus(z1) -> A planes ; softplus'(z1) -> scratch ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(2);
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = q * 64 + cc * 16;
+      for (int cc = 0; cc < 8; ++cc) {
+        const int col0 = q * 128 + cc * 16;
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
@@ -463,19 +536,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
               const uint32_t lo16 = __float2uint_rn(sg[u8 * 8 + 2 * e2] * 65535.0f), hi16 = __float2uint_rn(sg[u8 * 8 + 2 * e2 + 1] * 65535.0f);
               pk[e2] = lo16 | (hi16 << 16);
             }
-            st_stream(reinterpret_cast<uint8_t*>(sig_s) + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
+            st_stream(sig_s + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
           }
         }
       }
       tc_wait_st();
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
+      epi_arrive();
       TC_STAMP(3);
-      if (a.mode == 0) { encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next); encode_slice<P>(a, next_tile, 6, row, q, inA_next, enc_next); }
-      else {
-        encode_slice<P>(a, tile, 5, row, q, inA, enc_cur);          // this tile's static colour columns, in place (G0 is done)
-        encode_slice<P>(a, next_tile, 1, row, q, inA_next, enc_next);
-      }
 
       // ---------------- E1: h2 -> scratch planes (colour layer 0 input) ; sdf = W2[0,:] . h2 + b (fp32) ;
       //                      g2 = W2[0,:] * softplus'(z2) -> A planes (seed of the reverse sweep)
@@ -483,8 +550,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       TC_STAMP(4);
       float sdf_part = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = q * 64 + cc * 16;
+      for (int cc = 0; cc < 8; ++cc) {
+        const int col0 = q * 128 + cc * 16;
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
@@ -520,29 +587,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
       }
       tc_wait_st();
       red[q * 128 + row] = sdf_part;
-      tc_fence_before();
-      if (a.mode != 0) named_arrive(1, kEpiThreads + 32);
+      if (a.mode != 0) epi_arrive(); else tc_fence_before();
       TC_STAMP(5);
       named_sync(2, kEpiThreads);
-      float sdf = (red[row] + red[128 + row]) + (red[256 + row] + red[384 + row]) + sdf_bias;
+      const float sdf = (red[row] + red[128 + row]) + sdf_bias;
       if (q == 0 && valid && a.out.sdf) a.out.sdf[p] = sdf;
       if (a.mode == 0) {
-        named_sync(2, kEpiThreads);  // `red` is reused by the next tile; also orders the next tile's staged input
+        named_sync(2, kEpiThreads);  // `red` is reused by the next tile
         continue;
       }
-      encode_slice<P>(a, next_tile, 2, row, q, inA_next, enc_next);
-      TC_STAMP(6);
-      TC_STAMP(7);
 
       // ---------------- EB1: g1 = (W1^T g2) * softplus'(z1) -> A planes ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(8);
-#pragma unroll
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = q * 64 + cc * 16;
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        const int col0 = q * 128 + cc * 16;
         uint4 sp[2];
 #pragma unroll
-        for (int u8 = 0; u8 < 2; ++u8) sp[u8] = ld_stream_u4(reinterpret_cast<const uint8_t*>(sig_s) + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, pol_stream);
+        for (int u8 = 0; u8 < 2; ++u8) sp[u8] = ld_stream_u4(sig_s + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, pol_stream);
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
@@ -557,101 +620,101 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
       }
       tc_wait_st();
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
+      epi_arrive();
       TC_STAMP(9);
-      encode_slice<P>(a, next_tile, 3, row, q, inA_next, enc_next);
 
-      // ---------------- EB0: gin (96 cols) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ; geo feature reload
-      // the jacobian units and the geo-feature planes do not depend on this phase's MMA: fetch them before waiting
-      // thread (row, q) owns input columns [24 q, 24 q + 24); per column: x -> identity, PE -> one factor on its axis,
-      // grid -> 3 factors, padding -> 0.  Column classes are warp-uniform (q is), so there is no divergence.
+      // ---------------- EB0: gin (96 cols, kernel order) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ;
+      //                       h2 planes back into the A operand for colour layer 0
+      // thread (row, q) owns the operand chunks {0,1,4,5,8} (q = 0) / {2,3,6,7} (q = 1): two grid chunks + its share of PE / x
+      // (chunks 9..11 are zero padding).  The jacobian does not depend on this phase's MMA: the first chunk is fetched before the wait.
       const float* Jpe = reinterpret_cast<const float*>(enc_cur);
-      const float* Jg = Jpe + kMaxPe * 128;
+      const float* Jg = Jpe + kPeRows * 128;
       const int deg = a.pe_degree, half = 3 * deg;
-      const uint64_t pol_keep = l2_policy_evict_normal();
       float gx = 0.f, gy = 0.f, gz = 0.f;
-      uint32_t gin_v[8];
+#pragma unroll 1
+      for (int ci = 0; ci < 5; ++ci) {
+        const int ck = ci < 2 ? 2 * q + ci : (ci < 4 ? 4 + 2 * q + (ci - 2) : (q == 0 ? 8 : -1));
+        if (ck >= 0) {
+          float jx[8], jy[8], jz[8];
+          if (ck < 4) {
 #pragma unroll
-      for (int c8 = 0; c8 < 3; ++c8) {
-        const int c0 = q * 24 + c8 * 8;
-        // predicated (branch-free) fetch of this batch's jacobian entries: every load is issued before the first use
-        float jx[8], jy[8], jz[8];
+            for (int j = 0; j < 8; ++j) {
+              const int cg = ck * 8 + j;
+              const bool on = cg < a.grid_dim;
+              jx[j] = on ? ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_keep) : 0.f;
+              jy[j] = on ? ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_keep) : 0.f;
+              jz[j] = on ? ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_keep) : 0.f;
+            }
+          } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int c = c0 + j;
-          const bool is_pe = c >= 3 && c < 3 + a.pe_dim;
-          const bool is_grid = c >= 3 + a.pe_dim && c < a.in_dim;
-          const int i = c - 3, cg = c - 3 - a.pe_dim;
-          const int ia = i >= half ? i - half : i;                       // axis block of a PE column
-          const float dv = is_pe ? ld_stream_f1(Jpe + i * 128 + row, pol_keep) : 0.f;
-          const float g0 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_keep) : 0.f;
-          const float g1 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_keep) : 0.f;
-          const float g2 = is_grid ? ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_keep) : 0.f;
-          jx[j] = c == 0 ? 1.f : (is_pe && ia < deg ? dv : g0);
-          jy[j] = c == 1 ? 1.f : (is_pe && ia >= deg && ia < 2 * deg ? dv : g1);
-          jz[j] = c == 2 ? 1.f : (is_pe && ia >= 2 * deg ? dv : g2);
-        }
-        if (c8 == 0) {
-          mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-          TC_STAMP(10);
-        }
-        tmem_ld8(d_tmem + lane_addr + c0, gin_v);
-        tc_wait_ld();
+            for (int j = 0; j < 8; ++j) {
+              const int i = ck * 8 + j - 32;
+              const bool is_pe = i < a.pe_dim;
+              const int ia = i >= half ? i - half : i;                       // axis block of a PE column
+              const int xj = i - a.pe_dim;                                   // 0..2: the x columns
+              const float dv = is_pe ? ld_stream_f1(Jpe + i * 128 + row, pol_keep) : 0.f;
+              jx[j] = is_pe ? (ia < deg ? dv : 0.f) : (xj == 0 ? 1.f : 0.f);
+              jy[j] = is_pe ? ((ia >= deg && ia < 2 * deg) ? dv : 0.f) : (xj == 1 ? 1.f : 0.f);
+              jz[j] = is_pe ? (ia >= 2 * deg ? dv : 0.f) : (xj == 2 ? 1.f : 0.f);
+            }
+          }
+          if (ci == 0) {
+            mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+            TC_STAMP(10);
+          }
+          uint32_t gin_v[8];
+          tmem_ld8(d_tmem + lane_addr + ck * 8, gin_v);
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float g = __uint_as_float(gin_v[j]);
-          gx = fmaf(g, jx[j], gx); gy = fmaf(g, jy[j], gy); gz = fmaf(g, jz[j], gz);
+          for (int j = 0; j < 8; ++j) {
+            const float g = __uint_as_float(gin_v[j]);
+            gx = fmaf(g, jx[j], gx); gy = fmaf(g, jy[j], gy); gz = fmaf(g, jz[j], gz);
+          }
         }
       }
-      red[(0 * 4 + q) * 128 + row] = gx; red[(1 * 4 + q) * 128 + row] = gy; red[(2 * 4 + q) * 128 + row] = gz;
-      // h2 planes back into the A operand for colour layer 0 (all L2 loads in flight before the first TMEM store)
-      {
+      red[(0 * 2 + q) * 128 + row] = gx; red[(1 * 2 + q) * 128 + row] = gy; red[(2 * 2 + q) * 128 + row] = gz;
+      // h2 planes back into the A operand for colour layer 0 (two batches of 8 units: all L2 loads of a batch in flight together)
+#pragma unroll 1
+      for (int hb = 0; hb < 2; ++hb) {
         uint4 gh[8], gl[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const size_t unit = ((size_t)(q * 8 + u) * 128 + row) * 16;
+          const size_t unit = ((size_t)(q * 16 + hb * 8 + u) * 128 + row) * 16;
           gh[u] = ld_stream_u4(gf_s + unit, pol_stream);
           if (P > 1) gl[u] = ld_stream_u4(gf_s + 65536 + unit, pol_stream);
         }
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
           const uint32_t h8[8] = {gh[u].x, gh[u].y, gh[u].z, gh[u].w, gh[u + 1].x, gh[u + 1].y, gh[u + 1].z, gh[u + 1].w};
-          tmem_st8(a_tmem + lane_addr + (q * 8 + u) * 4, h8);
+          tmem_st8(a_tmem + lane_addr + (q * 16 + hb * 8 + u) * 4, h8);
           if (P > 1) {
             const uint32_t l8[8] = {gl[u].x, gl[u].y, gl[u].z, gl[u].w, gl[u + 1].x, gl[u + 1].y, gl[u + 1].z, gl[u + 1].w};
-            tmem_st8(a_tmem + 128 + lane_addr + (q * 8 + u) * 4, l8);
+            tmem_st8(a_tmem + 128 + lane_addr + (q * 16 + hb * 8 + u) * 4, l8);
           }
         }
       }
       named_sync(2, kEpiThreads);
-      const float grx = (red[(0 * 4 + 0) * 128 + row] + red[(0 * 4 + 1) * 128 + row]) + (red[(0 * 4 + 2) * 128 + row] + red[(0 * 4 + 3) * 128 + row]);
-      const float gry = (red[(1 * 4 + 0) * 128 + row] + red[(1 * 4 + 1) * 128 + row]) + (red[(1 * 4 + 2) * 128 + row] + red[(1 * 4 + 3) * 128 + row]);
-      const float grz = (red[(2 * 4 + 0) * 128 + row] + red[(2 * 4 + 1) * 128 + row]) + (red[(2 * 4 + 2) * 128 + row] + red[(2 * 4 + 3) * 128 + row]);
+      const float grx = red[(0 * 2 + 0) * 128 + row] + red[(0 * 2 + 1) * 128 + row];
+      const float gry = red[(1 * 2 + 0) * 128 + row] + red[(1 * 2 + 1) * 128 + row];
+      const float grz = red[(2 * 2 + 0) * 128 + row] + red[(2 * 2 + 1) * 128 + row];
       const float gn = fmaxf(sqrtf(grx * grx + gry * gry + grz * grz), 1e-12f);      // F.normalize eps
       const float nx = grx / gn, ny = gry / gn, nz = grz / gn;
       if (q == 0) {
         // chunk 0 of the colour operand: [grad(3), n.v, 0, 0, 0, 0]   (sdf_field.py:572-584; columns re-ordered at pack time)
-        uint32_t hi[4], lo[4];
-        split2(grx, gry, hi[0], lo[0]);
-        split2(grz, a.use_n_dot_v ? nx * dirx + ny * diry + nz * dirz : 0.f, hi[1], lo[1]);
-        hi[2] = hi[3] = lo[2] = lo[3] = 0u;
-        *reinterpret_cast<uint4*>(inA + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        const float c0v[8] = {grx, gry, grz, a.use_n_dot_v ? nx * dirx + ny * diry + nz * dirz : 0.f, 0.f, 0.f, 0.f, 0.f};
+        store_chunk<P>(inA, row, 0, c0v);
       }
       tc_wait_st();
       fence_async_smem();
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
+      epi_arrive();
       TC_STAMP(11);
-      encode_slice<P>(a, next_tile, 4, row, q, inA_next, enc_next);
 
       // ---------------- EC0: relu -> A planes ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(12);
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int col0 = q * 64 + cc * 16;
+#pragma unroll 2
+      for (int cc = 0; cc < 8; ++cc) {
+        const int col0 = q * 128 + cc * 16;
         uint32_t v[16];
         tmem_ld16(d_tmem + lane_addr + col0, v);
         tc_wait_ld();
@@ -665,19 +728,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
       }
       tc_wait_st();
-      tc_fence_before();
-      named_arrive(1, kEpiThreads + 32);
+      epi_arrive();
       TC_STAMP(13);
-      encode_slice<P>(a, next_tile, 6, row, q, inA_next, enc_next);
 
       // ---------------- EC1: relu, last colour layer (256 -> 3) as fp32 dots ----------------
       mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
       TC_STAMP(14);
       {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) {
-          const int col0 = q * 64 + cc * 16;
+#pragma unroll 2
+        for (int cc = 0; cc < 8; ++cc) {
+          const int col0 = q * 128 + cc * 16;
           uint32_t v[16];
           tmem_ld16(d_tmem + lane_addr + col0, v);
           tc_wait_ld();
@@ -690,42 +751,141 @@ __global__ void __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constan
           }
         }
         named_sync(2, kEpiThreads);   // everyone has consumed the gradient partials in `red`
-        red[(0 * 4 + q) * 128 + row] = r0; red[(1 * 4 + q) * 128 + row] = r1; red[(2 * 4 + q) * 128 + row] = r2;
+        red[(0 * 2 + q) * 128 + row] = r0; red[(1 * 2 + q) * 128 + row] = r1; red[(2 * 2 + q) * 128 + row] = r2;
       }
       tc_fence_before();
       named_sync(2, kEpiThreads);
-      if (q == 0 && valid) {
+      if (q == 0) {
         // ---------------- per-point heads ----------------
-        if (a.out.rgb) {
+        float rgbv[3];
 #pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            const float raw = (red[(c * 4 + 0) * 128 + row] + red[(c * 4 + 1) * 128 + row]) + (red[(c * 4 + 2) * 128 + row] + red[(c * 4 + 3) * 128 + row]) + __ldg(b_c2 + c);
-            a.out.rgb[p * 3 + c] = sigmoidf_(raw) * (1.f + 2.f * a.rgb_padding) - a.rgb_padding;
-          }
+        for (int c = 0; c < 3; ++c) {
+          const float raw = (red[(c * 2 + 0) * 128 + row] + red[(c * 2 + 1) * 128 + row]) + __ldg(b_c2 + c);
+          rgbv[c] = sigmoidf_(raw) * (1.f + 2.f * a.rgb_padding) - a.rgb_padding;
         }
-        if (a.out.gradients) { a.out.gradients[p * 3] = grx; a.out.gradients[p * 3 + 1] = gry; a.out.gradients[p * 3 + 2] = grz; }
-        if (a.out.normals) { a.out.normals[p * 3] = nx; a.out.normals[p * 3 + 1] = ny; a.out.normals[p * 3 + 2] = nz; }
-        if (a.out.density) {
+        float density = 0.f, alpha = 0.f;
+        if (a.out.density || (a.rnd.enabled && a.rnd.from_density)) {
           const float beta = fabsf(__ldg(a.beta)) + __ldg(a.beta_min);
           const float sg = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
-          a.out.density[p] = (1.0f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(sdf) / beta));
+          density = (1.0f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(sdf) / beta));
         }
-        if (a.out.occupancy) a.out.occupancy[p] = sigmoidf_(-10.0f * sdf);
-        if (a.out.alpha) {
+        if (a.out.alpha || (a.rnd.enabled && !a.rnd.from_density)) {
           const float inv_s = fminf(fmaxf(expf(__ldg(a.variance) * 10.0f), 1e-6f), 1e6f);
           const float true_cos = dirx * grx + diry * gry + dirz * grz;
           const float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - a.cos_anneal) + fmaxf(-true_cos, 0.f) * a.cos_anneal);
           const float prev_cdf = sigmoidf_((sdf - iter_cos * delta * 0.5f) * inv_s), next_cdf = sigmoidf_((sdf + iter_cos * delta * 0.5f) * inv_s);
-          a.out.alpha[p] = fminf(fmaxf((prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f), 0.f), 1.f);
+          alpha = fminf(fmaxf((prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f), 0.f), 1.f);
+        }
+        if (valid) {
+          if (a.out.rgb) { a.out.rgb[p * 3] = rgbv[0]; a.out.rgb[p * 3 + 1] = rgbv[1]; a.out.rgb[p * 3 + 2] = rgbv[2]; }
+          if (a.out.gradients) { a.out.gradients[p * 3] = grx; a.out.gradients[p * 3 + 1] = gry; a.out.gradients[p * 3 + 2] = grz; }
+          if (a.out.normals) { a.out.normals[p * 3] = nx; a.out.normals[p * 3 + 1] = ny; a.out.normals[p * 3 + 2] = nz; }
+          if (a.out.density) a.out.density[p] = density;
+          if (a.out.occupancy) a.out.occupancy[p] = sigmoidf_(-10.0f * sdf);
+          if (a.out.alpha) a.out.alpha[p] = alpha;
+        }
+        if (a.rnd.enabled) {
+          // ---------------- fused compositing: the tile holds 128 / S whole rays; row -> (ray, sample) = (row / S, row % S) ----------------
+          const int S = a.n_samples;
+          const int s_idx = row % S;
+          const int rl = row / S;                                   // ray within the tile
+          const bool dens = a.rnd.from_density != 0;
+          // factor by which the transmittance drops across this sample: 1 - alpha + 1e-7 (rays.py:204-206), or as an exponent
+          // delta * sigma for the density form (rays.py:160-170)
+          const float dd = valid ? __fmul_rn(delta, density) : 0.f;
+          double f = dens ? (double)dd : (valid ? (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f) : 1.0);
+          double incl = f;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const double o = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d && s_idx >= d) incl = dens ? incl + o : incl * o;
+          }
+          double excl = __shfl_up_sync(0xffffffffu, incl, 1);
+          if (lane == 0 || s_idx == 0) excl = dens ? 0.0 : 1.0;
+          if (lane == 31) wtot[wq] = incl;
+          named_sync(3, 128);
+          if (S > 32) {
+            const int first = (wq * 32 / S) * (S / 32);
+            for (int w2 = first; w2 < wq; ++w2) excl = dens ? excl + wtot[w2] : excl * wtot[w2];
+          }
+          const float T = dens ? expf(-(float)excl) : (float)excl;
+          const float al = dens ? __fsub_rn(1.0f, expf(-dd)) : alpha;
+          const float w = valid ? __fmul_rn(al, T) : 0.f;
+          const float mid = __fdiv_rn(__fadd_rn(pg.t0, pg.t1), 2.0f);            // (starts + ends) / 2, renderers.py:247
+          if (valid && a.rnd.weights) a.rnd.weights[p] = w;
+          float vs[8] = {w, w * rgbv[0], w * rgbv[1], w * rgbv[2], w * nx, w * ny, w * nz, w * mid};
+          float smin = valid ? mid : INFINITY, smax = valid ? mid : -INFINITY;
+          const int span = S < 32 ? S : 32;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            if (d < span) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vs[k] += __shfl_down_sync(0xffffffffu, vs[k], d);
+            }
+            smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, d));
+            smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
+          }
+          if (a.rnd.steps_minmax && lane == 0 && smin <= smax) { atomic_min_float(a.rnd.steps_minmax, smin); atomic_max_float(a.rnd.steps_minmax + 1, smax); }
+          if (S > 32) {
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) atomicAdd(&racc[k * 4 + rl], vs[k]);
+            }
+            if (s_idx == S - 1) { lastrgb[rl * 3] = rgbv[0]; lastrgb[rl * 3 + 1] = rgbv[1]; lastrgb[rl * 3 + 2] = rgbv[2]; }
+            named_sync(3, 128);
+            if (s_idx == 0) {
+#pragma unroll
+              for (int k = 0; k < 8; ++k) { vs[k] = racc[k * 4 + rl]; racc[k * 4 + rl] = 0.f; }
+            }
+          }
+          // transmittance after the last sample (alphas: transmittance[:, -1] = bg_transmittance, neus.py:101) / before it (densities: volsdf.py:67-68)
+          double tot;
+          float lr, lg, lb;
+          if (S > 32) {
+            const int first = (wq * 32 / S) * (S / 32);
+            tot = dens ? 0.0 : 1.0;
+            const int nw = dens ? S / 32 - 1 : S / 32;
+            for (int w2 = first; w2 < first + nw; ++w2) tot = dens ? tot + wtot[w2] : tot * wtot[w2];
+            lr = lastrgb[rl * 3]; lg = lastrgb[rl * 3 + 1]; lb = lastrgb[rl * 3 + 2];
+          } else {
+            const int last = (lane - s_idx) + S - 1;
+            tot = __shfl_sync(0xffffffffu, dens ? excl : incl, last);
+            lr = __shfl_sync(0xffffffffu, rgbv[0], last); lg = __shfl_sync(0xffffffffu, rgbv[1], last); lb = __shfl_sync(0xffffffffu, rgbv[2], last);
+          }
+          if (S > 32 && dens) {
+            // exclusive sum at the last sample of the ray = transmittance exponent before the last sample; it lives in the last warp of the ray
+            if (s_idx == S - 1) wtot[wq] = excl;       // (wtot of the ray's last warp is no longer needed by anyone else)
+            named_sync(3, 128);
+            tot = wtot[(wq * 32 / S) * (S / 32) + S / 32 - 1];
+          }
+          const long long ray = (long long)tile * (128 / S) + rl;
+          if (s_idx == 0 && ray * S < a.n_points) {
+            const float acc = vs[0];
+            if (a.rnd.rgb) {
+              float bgc[3] = {0.f, 0.f, 0.f};
+              if (a.rnd.bg_mode == SDFB200_BG_COLOR) { bgc[0] = a.rnd.bg[0]; bgc[1] = a.rnd.bg[1]; bgc[2] = a.rnd.bg[2]; }
+              else if (a.rnd.bg_mode == SDFB200_BG_PER_RAY) { bgc[0] = a.rnd.bg[ray * 3]; bgc[1] = a.rnd.bg[ray * 3 + 1]; bgc[2] = a.rnd.bg[ray * 3 + 2]; }
+              else { bgc[0] = lr; bgc[1] = lg; bgc[2] = lb; }
+              const float rem = 1.0f - acc;
+              const float o[3] = {vs[1] + bgc[0] * rem, vs[2] + bgc[1] * rem, vs[3] + bgc[2] * rem};
+#pragma unroll
+              for (int c = 0; c < 3; ++c) a.rnd.rgb[ray * 3 + c] = a.rnd.clamp01 ? fminf(fmaxf(o[c], 0.f), 1.f) : o[c];
+            }
+            if (a.rnd.accumulation) a.rnd.accumulation[ray] = acc;
+            if (a.rnd.normal) { a.rnd.normal[ray * 3] = vs[4]; a.rnd.normal[ray * 3 + 1] = vs[5]; a.rnd.normal[ray * 3 + 2] = vs[6]; }
+            if (a.rnd.depth) a.rnd.depth[ray] = vs[7] / (acc + 1e-10f);
+            if (a.rnd.bg_transmittance) a.rnd.bg_transmittance[ray] = dens ? expf(-(float)tot) : (float)tot;
+          }
         }
       }
-      named_sync(2, kEpiThreads);     // `red` is rewritten by the next tile; orders the staged input / scratch of the next tile
+      named_sync(2, kEpiThreads);     // `red` / `racc` are rewritten by the next tile
       TC_STAMP(15);
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  cluster_sync_all();                 // no CTA of the pair may release its TMEM / exit while the other one's MMAs could still touch it
+  if (warp == 0) tmem_dealloc2<512>(tmem);
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -737,12 +897,10 @@ struct TcPlan {
   int planes;
   TcLayer layer[L_COUNT];
   size_t total, wc_off, bc_off;
-  int cm_dim;
 };
 
 static void make_tc_plan(const sdfb200_field_t& f, const FieldPlan& p, TcPlan& t) {
   t.planes = f.precision == SDFB200_PRECISION_BF16X3 ? 2 : 1;
-  t.cm_dim = 3 + 27 + 3 + f.appearance_dim + (f.use_n_dot_v ? 1 : 0);
   const int np[L_COUNT] = {256, 256, 256, kInK, 256, 256, 256};
   const int nkb[L_COUNT] = {kInK / kKB, 8, 8, 8, 8, kInK / kKB, 8};
   size_t off = p.tc_off;
@@ -764,11 +922,16 @@ bool field_tc_supported(const sdfb200_field_t& f, const FieldPlan& p) {
   if (p.n_geo != 3 || p.n_col != 3) return false;
   if (p.geo[0].N != 256 || p.geo[1].N != 256 || p.geo_feat != 256 || p.col[0].N != 256 || p.col[1].N != 256) return false;
   if (f.use_numerical_gradients || f.off_axis || f.use_diffuse_color || f.use_specular_tint || f.use_reflections) return false;
-  if (p.in_dim > kInK || p.grid_dim > kMaxGridDim || p.pe_dim > kMaxPe) return false;
+  if (p.grid_dim > kMaxGridDim || p.pe_dim > kMaxPe || 32 + p.pe_dim + 3 > kInK) return false;
+  if (f.pe_degree < 1) return false;
   if (f.use_grid_feature && f.grid.n_features != 2) return false;
-  const int cm = 3 + 27 + 3 + f.appearance_dim + (f.use_n_dot_v ? 1 : 0);
   if (38 + f.appearance_dim > kInK) return false;
   return true;
+}
+
+// fused compositing needs whole rays inside a 128-point tile
+bool field_tc_render_supported(const sdfb200_field_t& f, const FieldPlan& p, int n_samples) {
+  return field_tc_supported(f, p) && n_samples >= 1 && n_samples <= 128 && (128 % n_samples) == 0;
 }
 
 size_t field_tc_packed_bytes(const sdfb200_field_t& f, const FieldPlan& p) {
@@ -776,8 +939,6 @@ size_t field_tc_packed_bytes(const sdfb200_field_t& f, const FieldPlan& p) {
   make_tc_plan(f, p, t);
   return t.total;
 }
-
-
 
 size_t field_tc_workspace_floats(const sdfb200_field_t& f, const FieldPlan&, int64_t) {
   const int planes = f.precision == SDFB200_PRECISION_BF16X3 ? 2 : 1;
@@ -787,41 +948,56 @@ size_t field_tc_workspace_floats(const sdfb200_field_t& f, const FieldPlan&, int
 int field_tc_pack(const sdfb200_field_t& f, const FieldPlan& p, char* blob, cudaStream_t st) {
   TcPlan t;
   make_tc_plan(f, p, t);
-  ColMap ident;
+  IdxMap ident;
   for (int i = 0; i < kInK; ++i) ident.src[i] = (short)i;
-  auto pack = [&](int L, const float* W, int ldw, int N, int K, const ColMap* map) -> int {
+  auto pack = [&](int L, const float* W, int ldw, int N, int K, const IdxMap* colmap, const IdxMap* rowmap) -> int {
     const TcLayer& ly = t.layer[L];
     const int tot = ly.nkb * ly.Np * kKB;
-    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, t.planes, map != nullptr, map ? *map : ident, (__nv_bfloat16*)(blob + ly.w_off));
+    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, t.planes, colmap != nullptr, colmap ? *colmap : ident, rowmap != nullptr,
+                                                 rowmap ? *rowmap : ident, (__nv_bfloat16*)(blob + ly.w_off));
     SDFB_LAUNCHED("k_tc_pack");
     return 0;
   };
   const LayerPlan &g0 = p.geo[0], &g1 = p.geo[1], &g2 = p.geo[2], &c0 = p.col[0], &c1 = p.col[1];
+  // geo input, kernel column order [grid(32) | PE | x | 0]  <-  reference order [x(3) | PE | grid]  (sdf_field.py:391-396)
+  IdxMap gin;
+  for (int i = 0; i < kInK; ++i) gin.src[i] = -1;
+  for (int i = 0; i < p.grid_dim; ++i) gin.src[i] = (short)(3 + p.pe_dim + i);
+  for (int i = 0; i < p.pe_dim; ++i) gin.src[32 + i] = (short)(3 + i);
+  for (int i = 0; i < 3; ++i) gin.src[32 + p.pe_dim + i] = (short)i;
   int r;
-  if ((r = pack(L_G0, (const float*)(blob + g0.w_off), g0.Kp, 256, g0.K, nullptr))) return r;
-  if ((r = pack(L_G1, (const float*)(blob + g1.w_off), g1.Kp, 256, 256, nullptr))) return r;
-  if ((r = pack(L_B1, (const float*)(blob + g1.wt_off), g1.Np, 256, 256, nullptr))) return r;              // W1^T: [in][out]
-  if ((r = pack(L_B0, (const float*)(blob + g0.wt_off), g0.Np, g0.K, 256, nullptr))) return r;             // W0^T: rows = input index
+  if ((r = pack(L_G0, (const float*)(blob + g0.w_off), g0.Kp, 256, g0.K, &gin, nullptr))) return r;
+  if ((r = pack(L_G1, (const float*)(blob + g1.w_off), g1.Kp, 256, 256, nullptr, nullptr))) return r;
+  if ((r = pack(L_B1, (const float*)(blob + g1.wt_off), g1.Np, 256, 256, nullptr, nullptr))) return r;          // W1^T: [in][out]
+  if ((r = pack(L_B0, (const float*)(blob + g0.wt_off), g0.Np, g0.K, 256, nullptr, &gin))) return r;            // W0^T: rows = input index (kernel order)
   // colour layer 0 (sdf_field.py:572-584): reference input = [x(3) dir(27) grad(3) | geo feature(256) | appearance | n.v]
   k_fuse_c0<<<256, 256, 0, st>>>((const float*)(blob + c0.w_off), c0.Kp, (const float*)(blob + c0.b_off), (const float*)(blob + g2.w_off), g2.Kp,
                                  (const float*)(blob + g2.b_off), (float*)(blob + t.wc_off), (float*)(blob + t.bc_off));
   SDFB_LAUNCHED("k_fuse_c0");
-  if ((r = pack(L_C0H, (const float*)(blob + t.wc_off), 256, 256, 256, nullptr))) return r;
+  if ((r = pack(L_C0H, (const float*)(blob + t.wc_off), 256, 256, 256, nullptr, nullptr))) return r;
   // misc operand, kernel order: chunk 0 = [grad(3), n.v, 0 x4] (written per tile by the epilogue), then the static part
-  // [x(3), dir-enc(27), appearance] prepared by the encoder warps
-  ColMap cm;
+  // [x(3), dir-enc(27), appearance] prepared by the gather warps
+  IdxMap cm;
   for (int i = 0; i < kInK; ++i) cm.src[i] = -1;
   cm.src[0] = 30; cm.src[1] = 31; cm.src[2] = 32;
   if (f.use_n_dot_v) cm.src[3] = (short)(289 + f.appearance_dim);
   for (int i = 0; i < 30; ++i) cm.src[8 + i] = (short)i;
   for (int i = 0; i < f.appearance_dim; ++i) cm.src[38 + i] = (short)(289 + i);
-  if ((r = pack(L_C0MISC, (const float*)(blob + c0.w_off), c0.Kp, 256, kInK, &cm))) return r;
-  if ((r = pack(L_C1, (const float*)(blob + c1.w_off), c1.Kp, 256, 256, nullptr))) return r;
+  if ((r = pack(L_C0MISC, (const float*)(blob + c0.w_off), c0.Kp, 256, kInK, &cm, nullptr))) return r;
+  if ((r = pack(L_C1, (const float*)(blob + c1.w_off), c1.Kp, 256, 256, nullptr, nullptr))) return r;
   return 0;
 }
 
+// grid size: two CTAs per cluster, one cluster per TPC; never more clusters than can be co-resident (the tile loop is static)
+static int tc_max_pairs() {
+  static int cached = 0;
+  if (cached) return cached;
+  cached = kNumSMs / 2;
+  return cached;
+}
+
 int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* blob, const void* table, const sdfb200_field_in_t& in,
-                     const sdfb200_field_out_t& out, float* ws, size_t ws_floats, cudaStream_t st) {
+                     const sdfb200_field_out_t& out, const TcRender* rnd, float* ws, size_t ws_floats, cudaStream_t st) {
   const int64_t N = in.n_rays * (int64_t)in.n_samples;
   if (N == 0) return 0;
   TcPlan t;
@@ -829,32 +1005,34 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   const size_t per_cta = kScratchPerCta(t.planes);
   if (ws_floats * sizeof(float) < (size_t)kNumSMs * per_cta) return fail(SDFB200_EWORKSPACE, "workspace too small for the tensor-core path%s", "", 0);
   SDFB_REQUIRE(out.geo_feature == nullptr, "geo_feature is not produced by the tensor-core path (use precision fp32)");
-  const bool sdf_only = out.sdf && !out.gradients && !out.normals && !out.rgb && !out.density && !out.alpha && !out.occupancy;
+  const bool render = rnd != nullptr && rnd->enabled;
+  const bool sdf_only = !render && out.sdf && !out.gradients && !out.normals && !out.rgb && !out.density && !out.alpha && !out.occupancy;
   if (!sdf_only) {
-    if (out.rgb || out.alpha) SDFB_REQUIRE(in.directions != nullptr, "directions required for rgb / alpha");
-    if (out.alpha) SDFB_REQUIRE(in.bins != nullptr && in.variance != nullptr, "alpha needs bins and the variance parameter");
-    if (out.density) SDFB_REQUIRE(in.beta != nullptr && in.beta_min != nullptr, "density needs beta and beta_min");
+    if (out.rgb || out.alpha || render) SDFB_REQUIRE(in.directions != nullptr, "directions required for rgb / alpha");
+    if (out.alpha || (render && !rnd->from_density)) SDFB_REQUIRE(in.bins != nullptr && in.variance != nullptr, "alpha needs bins and the variance parameter");
+    if (out.density || (render && rnd->from_density)) SDFB_REQUIRE(in.beta != nullptr && in.beta_min != nullptr, "density needs beta and beta_min");
   }
+  if (render) SDFB_REQUIRE(in.bins != nullptr && (128 % in.n_samples) == 0, "fused compositing needs bins and 128 % n_samples == 0");
   SDFB_REQUIRE(out.sampled_sdf == nullptr, "sampled_sdf is only produced with use_numerical_gradients");
   TcArgs a;
   a.grid = f.grid;
   for (int l = 0; l < L_COUNT; ++l) a.layer[l] = t.layer[l];
   a.use_grid = f.use_grid_feature; a.pe_degree = f.pe_degree; a.use_pe = f.use_position_encoding;
   a.contraction = in.apply_contraction ? f.contraction : SDFB200_CONTRACT_NONE;
-  a.in_dim = p.in_dim; a.pe_dim = p.pe_dim; a.grid_dim = p.grid_dim; a.cm_dim = t.cm_dim; a.app_dim = f.appearance_dim; a.use_n_dot_v = f.use_n_dot_v;
+  a.in_dim = p.in_dim; a.pe_dim = p.pe_dim; a.grid_dim = p.grid_dim; a.app_dim = f.appearance_dim; a.use_n_dot_v = f.use_n_dot_v;
   a.mode = sdf_only ? 0 : 1;
-  a.timing = getenv("SDFB200_TC_TIMING") != nullptr;
-  a.pol_table = getenv("SDFB200_POL_TABLE") ? atoi(getenv("SDFB200_POL_TABLE")) : 2;
-  a.pol_scratch = getenv("SDFB200_POL_SCRATCH") ? atoi(getenv("SDFB200_POL_SCRATCH")) : 1;
   a.n_samples = in.n_samples; a.has_bins = in.bins != nullptr; a.n_points = N; a.n_tiles = (int)ceil_div(N, 128);
+  a.n_tile_pairs = (a.n_tiles + 1) / 2;
   a.rgb_padding = f.rgb_padding; a.cos_anneal = in.cos_anneal_ratio;
   a.origins = in.origins; a.directions = in.directions; a.bins = in.bins; a.appearance = in.appearance; a.variance = in.variance; a.beta = in.beta;
   a.beta_min = in.beta_min; a.table = table; a.blob = blob;
   a.b_g0 = p.geo[0].b_off; a.b_g1 = p.geo[1].b_off; a.b_g2 = p.geo[2].b_off; a.w_g2 = p.geo[2].w_off;
   a.b_c0 = t.bc_off; a.b_c1 = p.col[1].b_off; a.w_c2 = p.col[2].w_off; a.b_c2 = p.col[2].b_off;
   a.scratch = reinterpret_cast<char*>(ws); a.scratch_per_cta = per_cta; a.out = out;
-  const int grid = a.n_tiles < kNumSMs ? a.n_tiles : kNumSMs;
-  const size_t smem = 2 * (size_t)t.planes * (kInK / 8) * 2048 + (size_t)kStages * t.planes * 256 * kKB * 2 + 12 * 128 * 4 + 9 * 256 * 4 + 1024;
+  if (render) a.rnd = *rnd; else { a.rnd = TcRender{}; a.rnd.enabled = 0; }
+  const int pairs = a.n_tile_pairs < tc_max_pairs() ? a.n_tile_pairs : tc_max_pairs();
+  const int grid = 2 * pairs;
+  const size_t smem = 2 * (size_t)t.planes * (kInK / 8) * 2048 + (size_t)kStages * t.planes * 128 * kKB * 2 + (6 * 128 + 9 * 256 + 32 + 12) * 4 + 1024;
   if (t.planes == 2) {
     SDFB_CUDA(cudaFuncSetAttribute(k_field_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_field_tc<2><<<grid, kTcThreads, smem, st>>>(a);
@@ -868,7 +1046,9 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
 
 }  // namespace sdfb200
 
+#ifdef SDFB200_TC_TIMING
 extern "C" int sdfb200_debug_tc_timing(long long* host_out_512) {
   SDFB_CUDA(cudaMemcpyFromSymbol(host_out_512, sdfb200::g_tc_timing, sizeof(long long) * 512));
   return 0;
 }
+#endif

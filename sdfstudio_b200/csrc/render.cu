@@ -35,25 +35,6 @@ __global__ void __launch_bounds__(128) k_weights_from_density(const float* __res
   }
 }
 
-__device__ __forceinline__ void atomic_min_float(float* addr, float v) {
-  int* ia = reinterpret_cast<int*>(addr);
-  int old = *ia;
-  while (__int_as_float(old) > v) {
-    const int assumed = old;
-    old = atomicCAS(ia, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-__device__ __forceinline__ void atomic_max_float(float* addr, float v) {
-  int* ia = reinterpret_cast<int*>(addr);
-  int old = *ia;
-  while (__int_as_float(old) < v) {
-    const int assumed = old;
-    old = atomicCAS(ia, assumed, __float_as_int(v));
-    if (old == assumed) break;
-  }
-}
-
 struct RenderArgs {
   const float* weights; const float* rgb; const float* normals; const float* eu; const float* bg;
   int bg_mode, clamp01, depth_median; int64_t R; int S;

@@ -3,6 +3,7 @@
 // shared memory (SS) or in tensor memory (TS), weights streamed through a 2-stage ring by 1-D bulk copies, accumulator
 // in TMEM read back with tcgen05.ld.  Lets the descriptors / layouts be validated in isolation on the GPU.
 #include "tc_common.cuh"
+#include "../../include/sdfb200_debug.h"
 
 namespace sdfb200 {
 using namespace tc;
@@ -168,4 +169,16 @@ extern "C" int sdfb200_debug_tc_gemm(const float* A, const float* W, int32_t K, 
 #undef LAUNCH
   SDFB_LAUNCHED("k_tc_gemm_test");
   return 0;
+}
+
+// building-block test of the generic tcgen05 Linear (tc_linear.cu) against a reference GEMM: same arguments as the internal sgemm()
+namespace sdfb200 {
+int tc_gemm(int planes, int epi, const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M, int Np, int Kp,
+            const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st);
+}
+extern "C" int sdfb200_debug_tc_linear(int32_t planes, int32_t epi, const float* X, int32_t ldx, const float* W, const float* bias, float* Y,
+                                       int32_t ldy, int64_t M, int32_t Np, int32_t Kp, const float* aux, int32_t ldaux, int32_t aux_cols,
+                                       void* scratch, void* stream) {
+  SDFB_REQUIRE(X && W && Y && scratch && M >= 0, "NULL pointer");
+  return tc_gemm(planes, epi, X, ldx, W, bias, Y, ldy, M, Np, Kp, aux, ldaux, aux_cols, scratch, (cudaStream_t)stream);
 }

@@ -380,6 +380,91 @@ class SDFField(nn.Module):
                    "sdfb200_field_forward")
         return outs
 
+    _SAMPLE_SHAPES = {"sdf": 1, "gradients": 3, "normals": 3, "rgb": 3, "density": 1, "alpha": 1, "occupancy": 1, "points_norm": 1, "points": 3}
+
+    @torch.no_grad()
+    def render(self, ray_samples, background, from_density: bool = False, training: bool = False, want_weights: bool = True,
+               sample_outputs=(), clip_depth: bool = True) -> Dict[str, torch.Tensor]:
+        """``get_outputs`` + weights + RGB / expected-depth / normal / accumulation renderers in ONE library call
+        (sdfb200_field_render): what ``SurfaceModel.get_outputs`` computes between the sampler and the losses
+        (models/base_surface_model.py:292-365; NeuS alphas, models/neus.py:85-116, or ``from_density`` = VolSDF's Laplace
+        density weights, models/volsdf.py:62-87).  On the fused tensor-core path the per-sample heads never touch HBM unless they
+        are asked for through ``sample_outputs`` (names of sdfb200_field_out_t).  Inference only (no autograd).
+        Returns rgb [R,3], depth [R,1], normal [R,3], accumulation [R,1], bg_transmittance [R,1] (+ weights [R,S,1], + per-sample heads)."""
+        if ray_samples.camera_indices is None:
+            raise AttributeError("Camera indices are not provided.")
+        lib = _lib.load()
+        origins, directions = rays_of(ray_samples)
+        bins = bins_of(ray_samples)
+        R, S = origins.shape[0], bins.shape[1] - 1
+        N = R * S
+        dev = origins.device
+        if dev.type != "cuda":
+            raise RuntimeError("sdfstudio_b200.SDFField runs on CUDA only (there is no CPU path)")
+        desc = self._field_desc()
+        packed = self._packed_weights(desc)
+        nbytes = lib.sdfb200_field_render_workspace_bytes(desc, R, S)
+        if nbytes == 0:
+            _lib.check(-1, "sdfb200_field_render_workspace_bytes")
+        if self._workspace is None or self._workspace.numel() < nbytes or self._workspace.device != dev:
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = self._workspace
+        # one flat output allocation: per-ray block [R, 9] = rgb(3) depth normal(3) accumulation bg_transmittance | minmax(2) | per-sample blocks
+        widths = [self._SAMPLE_SHAPES[k] for k in sample_outputs]
+        flat = torch.empty(R * 9 + 2 + N * (sum(widths) + (1 if want_weights else 0)), device=dev, dtype=torch.float32)
+        mm = flat[R * 9: R * 9 + 2]
+        if getattr(self, "_mm_init", None) is None or self._mm_init.device != dev:
+            self._mm_init = torch.tensor([float("inf"), float("-inf")], device=dev)
+        mm.copy_(self._mm_init)
+        off = R * 9 + 2
+        fout = _lib.FieldOut()
+        res = {}
+        for k, w_ in zip(sample_outputs, widths):
+            t = flat[off: off + N * w_]
+            off += N * w_
+            setattr(fout, k, t.data_ptr())
+            res[k] = t.view(R, S, w_)
+        rnd = _lib.FieldRender()
+        rnd.from_density, rnd.clamp01, rnd.clip_depth = int(from_density), int(not training), int(clip_depth)
+        bg_t = None
+        if isinstance(background, str):
+            if background == "last_sample":
+                rnd.bg_mode = _lib.BG_LAST_SAMPLE
+            elif background == "random":
+                rnd.bg_mode, bg_t = _lib.BG_PER_RAY, torch.rand(R, 3, device=dev)
+            else:
+                raise ValueError(f"unknown background {background!r}")
+        else:
+            bg_t = _lib.f32c(torch.as_tensor(background, dtype=torch.float32).to(dev))
+            rnd.bg_mode = _lib.BG_PER_RAY if bg_t.dim() == 2 else _lib.BG_COLOR
+        rnd.bg = _lib.ptr(bg_t)
+        if want_weights:
+            wt = flat[off: off + N]
+            rnd.weights = wt.data_ptr()
+            res["weights"] = wt.view(R, S, 1)
+        # per-ray outputs are stored planar ([3,R] etc. would not match the ABI) -> carve row-major [R,3] blocks instead
+        rgb = flat[: R * 3].view(R, 3)
+        nrm = flat[R * 3: R * 6].view(R, 3)
+        depth, acc, bgT = flat[R * 6: R * 7], flat[R * 7: R * 8], flat[R * 8: R * 9]
+        rnd.bg_transmittance = bgT.data_ptr()
+        rnd.out.rgb, rnd.out.normal, rnd.out.depth, rnd.out.accumulation, rnd.out.steps_minmax = (rgb.data_ptr(), nrm.data_ptr(), depth.data_ptr(),
+                                                                                                   acc.data_ptr(), mm.data_ptr())
+        fin = _lib.FieldIn()
+        fin.n_rays, fin.n_samples, fin.apply_contraction = R, S, 1
+        fin.origins, fin.directions, fin.bins = _lib.ptr(origins), _lib.ptr(directions), _lib.ptr(bins)
+        app = self._appearance(ray_samples.camera_indices, R, dev)
+        fin.appearance = _lib.ptr(app)
+        fin.variance = _lib.ptr(self.deviation_network.variance.detach())
+        fin.beta = _lib.ptr(self.laplace_density.beta.detach())
+        fin.beta_min = _lib.ptr(self.laplace_density.beta_min.detach())
+        fin.cos_anneal_ratio = float(self._cos_anneal_ratio)
+        fin.numerical_delta = float(self.numerical_gradients_delta)
+        table = self.encoding.compute_table() if self.use_grid_feature else None
+        _lib.check(lib.sdfb200_field_render(desc, _lib.ptr(packed), _lib.ptr(table), fin, fout, rnd, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()),
+                   "sdfb200_field_render")
+        res.update({"rgb": rgb, "depth": depth[:, None], "normal": nrm, "accumulation": acc[:, None], "bg_transmittance": bgT[:, None]})
+        return res
+
     def _differentiable(self) -> bool:
         """True when autograd is recording a training step: the methods below then return graph-carrying tensors from the
         autograd composition in sdf_field_train.py (grid operator = this package's kernels incl. double backward).  Everything

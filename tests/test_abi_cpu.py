@@ -34,7 +34,7 @@ def test_struct_sizes_match():
     from sdfstudio_b200 import _lib
 
     lib = _lib.load()
-    for which, st in enumerate((_lib.GridDesc, _lib.FieldDesc, _lib.FieldParams, _lib.FieldIn, _lib.FieldOut, _lib.RenderOut)):
+    for which, st in enumerate((_lib.GridDesc, _lib.FieldDesc, _lib.FieldParams, _lib.FieldIn, _lib.FieldOut, _lib.RenderOut, _lib.FieldRender)):
         assert lib.sdfb200_struct_size(which) == C.sizeof(st)
 
 

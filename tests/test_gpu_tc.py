@@ -11,14 +11,15 @@ pytestmark = pytest.mark.gpu
 def test_tc_gemm_tile(ts, planes, K, N):
     import sdfstudio_b200 as sb
 
-    lib = sb._lib.load()
+    lib = sb._lib.load_debug()
     g = torch.Generator().manual_seed(K * 1000 + N)
     A = torch.randn(128, K, generator=g).cuda()
     W = (torch.randn(N, K, generator=g) / K**0.5).cuda()
     Np = (N + 15) // 16 * 16
     D = torch.full((128, Np), float("nan"), device="cuda")
     scratch = torch.zeros((K // 32) * planes * Np * 64, dtype=torch.uint8, device="cuda")
-    sb._lib.check(lib.sdfb200_debug_tc_gemm(A.data_ptr(), W.data_ptr(), K, N, ts, planes, D.data_ptr(), scratch.data_ptr(), 0), "debug_tc_gemm")
+    rc = lib.sdfb200_debug_tc_gemm(A.data_ptr(), W.data_ptr(), K, N, ts, planes, D.data_ptr(), scratch.data_ptr(), 0)
+    assert rc == 0, lib.sdfb200_last_error_string()
     torch.cuda.synchronize()
     ref = (A.double() @ W.double().t()).float()
     scale = float((A.abs().double() @ W.abs().double().t()).max())
@@ -143,7 +144,7 @@ def test_field_fp16_table_matches_oracle_on_the_same_quantised_table(precision):
 def test_tc_linear_matches_fp64(planes, epi, M, Kp, Np):
     import sdfstudio_b200 as sb
 
-    lib = sb._lib.load()
+    lib = sb._lib.load_debug()
     g = torch.Generator().manual_seed(M + Kp + Np + epi)
     ldx, ldy = Kp + 16, Np + 32
     X = (torch.randn(M, ldx, generator=g) * 0.5).cuda()
@@ -153,8 +154,9 @@ def test_tc_linear_matches_fp64(planes, epi, M, Kp, Np):
     aux_cols = Np - 16
     Y = torch.full((M, ldy), float("nan"), device="cuda")
     scratch = torch.zeros(1 << 18, dtype=torch.uint8, device="cuda")
-    sb._lib.check(lib.sdfb200_debug_tc_linear(planes, epi, X.data_ptr(), ldx, W.data_ptr(), b.data_ptr(), Y.data_ptr(), ldy, M, Np, Kp, aux.data_ptr(),
-                                              Np, aux_cols, scratch.data_ptr(), 0), "debug_tc_linear")
+    rc = lib.sdfb200_debug_tc_linear(planes, epi, X.data_ptr(), ldx, W.data_ptr(), b.data_ptr(), Y.data_ptr(), ldy, M, Np, Kp, aux.data_ptr(), Np, aux_cols,
+                                     scratch.data_ptr(), 0)
+    assert rc == 0, lib.sdfb200_last_error_string()
     torch.cuda.synchronize()
     z = X[:, :Kp].double() @ W.double().t()
     if epi != 3:

@@ -149,3 +149,87 @@ def test_sdf_only_mode_multi_tile():
     s32 = o32.get_sdf(o[idx], d[idx], eu[:, :-1])
     s64 = o64.get_sdf(o[idx].double(), d[idx].double(), eu[:, :-1].double())
     assert_within_noise(sdf[idx.cuda()][..., 0], s32, s64, "get_sdf multi-tile", factor=4.0, floor=1e-4 * float(s64.abs().max()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# field + compositing in one call (sdfb200_field_render): fused into the tensor-core kernel when 128 % S == 0
+# ----------------------------------------------------------------------------------------------------------------
+def _unfused(sb, field, rs, bg, from_density, training=False):
+    H = sb.FieldHeadNames
+    out = field(rs, return_alphas=True)
+    if from_density:
+        w, T = rs.get_weights_and_transmittance(out[H.DENSITY])
+        img = sb.render_all(w, out[H.RGB], out[H.NORMAL], rs, bg, training=training)
+        img["weights"], img["bg_transmittance"] = w, T[:, -1, :]
+    else:
+        img = sb.render_from_alphas(out[H.ALPHA], out[H.RGB], out[H.NORMAL], rs, bg, training=training)
+    return out, img
+
+
+@pytest.mark.parametrize("S,R", [(128, 300), (64, 601), (32, 77), (16, 1000), (8, 33), (1, 200), (37, 50)])
+@pytest.mark.parametrize("from_density", [False, True])
+def test_fused_render_equals_field_plus_renderers(S, R, from_density):
+    """field.render (one kernel: heads + compositing in registers) against the separate field + renderer calls of the same
+    library on the same samples: identical per-sample arithmetic, compositing sums differ only in summation order."""
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200.synthetic import dtu_like_rays
+
+    field, _, _ = _bench_field("bf16x3")
+    o, d, cam, nears, fars = dtu_like_rays(R, 5 + S)
+    rb = make_bundle(o, d, cam, nears, fars)
+    bg = torch.tensor([0.9, 0.5, 0.1], device="cuda")
+    with torch.no_grad():
+        rs = sb.UniformSampler(num_samples=S).eval()(rb)
+        out, ref = _unfused(sb, field, rs, bg, from_density)
+        res = field.render(rs, bg, from_density=from_density, sample_outputs=("sdf", "gradients", "alpha"))
+    H = sb.FieldHeadNames
+    assert torch.equal(res["sdf"], out[H.SDF]) and torch.equal(res["gradients"], out[H.GRADIENT]) and torch.equal(res["alpha"], out[H.ALPHA])
+    torch.testing.assert_close(res["weights"], ref["weights"], rtol=2e-6, atol=1e-7)
+    for k in ("rgb", "depth", "normal", "accumulation", "bg_transmittance"):
+        torch.testing.assert_close(res[k], ref[k], rtol=1e-5, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("background", ["last_sample", "per_ray"])
+def test_fused_render_backgrounds_and_training_mode(background):
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200.synthetic import dtu_like_rays
+
+    field, _, _ = _bench_field("bf16x3")
+    R, S = 257, 64
+    o, d, cam, nears, fars = dtu_like_rays(R, 99)
+    rb = make_bundle(o, d, cam, nears, fars)
+    bg = "last_sample" if background == "last_sample" else torch.rand(R, 3, generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        rs = sb.UniformSampler(num_samples=S).eval()(rb)
+        out, ref = _unfused(sb, field, rs, bg, False, training=True)
+        res = field.render(rs, bg, training=True, want_weights=False)
+    assert "weights" not in res
+    for k in ("rgb", "depth", "normal", "accumulation"):
+        torch.testing.assert_close(res[k], ref[k], rtol=1e-5, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_fused_render_bench_config_vs_oracle():
+    """The benchmark step itself (4096 x 128, one fused launch) against the fp64 oracle on every 16th ray: rendered RGB / depth /
+    normal within 1e-4 relative (BASELINE north_star bound)."""
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200.synthetic import dtu_like_rays
+
+    field, o32, o64 = _bench_field("bf16x3")
+    R, S = 4096, 128
+    o, d, cam, nears, fars = dtu_like_rays(R, 1000)
+    rb = make_bundle(o, d, cam, nears, fars)
+    with torch.no_grad():
+        rs = sb.UniformSampler(num_samples=S).eval()(rb)
+        res = field.render(rs, torch.ones(3, device="cuda"))
+    idx = torch.arange(7, R, 16)
+    eu = sb.rays.bins_of(rs).cpu()
+    e32, e64, eu64 = _oracle_subset(o32, o64, o, d, cam, eu, idx)
+    ow, _ = samplers.weights_from_alphas(e64["alphas"][..., 0])
+    orgb = render.render_rgb(e64["rgb"], ow[..., None], torch.ones(3, dtype=torch.float64))
+    assert rel_err(res["rgb"][idx.cuda()], orgb, 1e-2) < 1e-4
+    gw, _ = samplers.weights_from_alphas(e32["alphas"][..., 0])
+    gdep = render.render_depth(gw[..., None], eu[idx][:, :-1, None], eu[idx][:, 1:, None], "expected")
+    odep = render.render_depth(ow[..., None], eu64[:, :-1, None], eu64[:, 1:, None], "expected")
+    assert_within_noise(res["depth"][idx.cuda()], gdep, odep, "fused/depth", factor=4.0, floor=1e-4 * float(odep.abs().max()))
+    assert rel_err(res["normal"][idx.cuda()], render.render_semantics(e64["normals"], ow[..., None]), 1e-1) < 1e-4
+    assert_within_noise(res["weights"][idx.cuda()][..., 0], gw, ow, "fused/weights", factor=4.0, floor=1e-5)

@@ -135,7 +135,7 @@ def test_weights_and_render_backward():
     dd = delta * d64[..., 0]
     Tr = torch.exp(-torch.cat([torch.zeros(R, 1, dtype=torch.float64), torch.cumsum(dd, 1)[:, :-1]], 1))
     wd = (1 - torch.exp(-dd)) * Tr
-    gd_r = torch.autograd.grad((wd * c_w[..., 0].double()).sum(), d64)[0]
+    gd_r = torch.autograd.grad((wd * c_w[..., 0].double()).sum(), d64, retain_graph=True)[0]
     dc = dens.cuda().requires_grad_(True)
     wc = weights_from_density(bins.cuda(), dc)
     assert _maxrel(wc[..., 0], wd) < 1e-5
