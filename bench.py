@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SDFB200_PRECISION", "auto"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--unfused", action="store_true", help="A/B: separate field and compositing launches (per-sample heads through HBM)")
     ap.add_argument("--table-dtype", default="fp32", choices=["fp32", "fp16"], help="fp16 = gather from a half-precision copy (tiny-cuda-nn's storage)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -240,11 +241,17 @@ def main():
         if time_field:
             e0, e1 = ev(), ev()
             e0.record()
-        out = field(rs, return_alphas=True)
+        if args.unfused:
+            out = field(rs, return_alphas=True)
+            if time_field:
+                e1.record()
+                field_ms.append((e0, e1))
+            return sb.render_from_alphas(out[H.ALPHA], out[H.RGB], out[H.NORMAL], rs, white)
+        res = field.render(rs, white)          # field + compositing: one fused launch (+ the global depth clip)
         if time_field:
             e1.record()
             field_ms.append((e0, e1))
-        return sb.render_from_alphas(out[H.ALPHA], out[H.RGB], out[H.NORMAL], rs, white)
+        return res
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 

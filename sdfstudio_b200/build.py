@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsdfb200.so")
 LIB_DEBUG = os.path.join(HERE, "libsdfb200_dbg.so")   # product objects + the building-block validation hooks (tests only)
-SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "tc_linear.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
+SOURCES = ["api.cu", "grid_encode.cu", "field_simt.cu", "field_tc.cu", "field_tc_p2_torch.cu", "field_tc_p2_tcnn.cu", "field_tc_p1_torch.cu", "field_tc_p1_tcnn.cu", "tc_linear.cu", "samplers.cu", "render.cu", "render_backward.cu", "density_field.cu", "rays_gen.cu"]
 DEBUG_SOURCES = ["tc_test.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
@@ -37,6 +37,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         (dbg_objs if s in DEBUG_SOURCES else objs).append(o)
         cmd = [NVCC, *FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    # the debug library carries a second build of the fused kernel with per-phase clock64 stamps (tools/tc_timing.py)
+    timing_obj = os.path.join(objdir, "field_tc_p2_torch_timing.o")
+    procs.append(("field_tc_p2_torch.cu [timing]", subprocess.Popen([NVCC, *FLAGS, "-DSDFB200_TC_TIMING", "-c", os.path.join(CSRC, "field_tc_p2_torch.cu"), "-o", timing_obj],
+                                                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for s, p in procs:
         out, _ = p.communicate()
@@ -48,7 +52,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print("\n".join(log))
     subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-lcudart"])
-    subprocess.check_call([NVCC, "-shared", "-o", LIB_DEBUG, *objs, *dbg_objs, "-lcudart"])
+    dbg_all = [o for o in objs if not o.endswith("field_tc_p2_torch.o")] + [timing_obj] + dbg_objs
+    subprocess.check_call([NVCC, "-shared", "-o", LIB_DEBUG, *dbg_all, "-lcudart"])
     return LIB
 
 

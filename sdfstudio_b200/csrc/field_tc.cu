@@ -1,105 +1,33 @@
-// Fused tcgen05 evaluation of the SDF field (SDFB200_PRECISION_BF16X3 / _BF16) for the neus-facto family of shapes:
-// geo MLP in-256-256-(1+256), colour MLP cin-256-256-3, analytic d sdf/dx, 2-feature hash grid (fp32 or fp16 table),
-// optionally followed IN THE SAME KERNEL by the per-ray compositing (alpha / density -> transmittance -> weights -> rgb, depth,
-// normal, accumulation: cameras/rays.py:131-230, model_components/renderers.py:53-118,171-261,284-295).
-//
-// Persistent CTA PAIRS (cluster of 2, tcgen05 cta_group::2): every CTA walks its own 128-point tiles, one MMA covers the two
-// tiles of a pair (M = 256) and each CTA streams only HALF of every weight tile (rows [0,N/2) / [N/2,N) of the B operand).
-// Per tile (everything stays on chip except three L2-resident spills):
-//   encode   4 gather warps (one thread per point), decoupled from the compute warps and one tile ahead: position,
-//            contraction, hash gathers (+ jacobian), PE -> bf16 split planes in smem (double buffered)
-//   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), next layer's A operand written to TMEM
-//   sdf      fp32 dot of h2 with row 0 of W2 on CUDA cores (exact fp32: the SDF drives NeuS alpha / Laplace density)
-//   (no G2)  the geo feature is linear in h2, so colour layer 0 is pre-multiplied at pack time: Wc = Wgf W2', and h2 itself
-//            (bf16 planes) takes the L2-resident round trip across the reverse sweep
-//   B1 B0    reverse sweep: g2 = W2[0,:]*sp'(z2), g1 = (W1^T g2)*sp'(z1), gin = W0^T g1;  sp'(z1) spilled at G0
-//   grad     d sdf/dx = gin_x + PE jacobian + grid jacobian / 4      (what autograd computes at sdf_field.py:647-654)
-//   C0 C1    relu MLP on [x, dir-enc, grad, geo feature, appearance]; last 256->3 layer as fp32 dots; sigmoid + padding
-//   heads    Laplace density, NeuS alpha, occupancy, normals; optional per-sample outputs
-//   render   (fused mode) segmented prefix product over the rays of the tile in double, weights, per-ray sums
-// MMA = tcgen05.mma kind::f16 (bf16 x bf16 -> fp32).  bf16x3: a0*w0 + a1*w0 + a0*w1 with a = a0+a1, w = w0+w1
-// (error ~2^-16 relative, fp32 accumulate).  Weights stream through a shared-memory ring filled by 1-D bulk copies (UBLKCP)
-// from a pre-packed image.  Warp roles: 0-7 epilogues (2 threads per row: 128 columns each), 8-11 gather/encode,
-// 12 weight producer, 13 MMA issuer (leader CTA) / weight-arrival relay (peer CTA).
-#include "field_plan.h"
-#include "grid.cuh"
+// Host side of the fused tensor-core field kernel (csrc/field_tc_kernel.cuh): packed-weight plan, weight packing kernels,
+// launch dispatch.  See field_tc_kernel.cuh for the kernel itself.
+#include "field_tc.h"
 #include "tc_common.cuh"
 
 namespace sdfb200 {
 using namespace tc;
 
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kGatherWarps = 4;
-constexpr int kWarpProducer = kEpiWarps + kGatherWarps;      // 12
-constexpr int kWarpMma = kWarpProducer + 1;                  // 13
-constexpr int kTcThreads = (kWarpMma + 1) * 32;              // 448
-constexpr int kStages = 6;
-constexpr int kKB = 32;           // K per streamed weight block
-constexpr int kMaxGridDim = 32;
-constexpr int kMaxPe = 60;        // PE columns (2 * 3 * degree), degree <= 10
-constexpr int kPeRows = 64;       // rows reserved for the PE jacobian in the scratch
-constexpr int kInK = 96;          // padded K of the two small-K operands (geo input, colour misc input)
-constexpr float kHalfPiF = 1.5707963267948966f;
-// kernel order of the geo input columns (K = 96): [grid features 0..31 | PE | x(3) | zero padding] -- every group of four hash
-// levels is one aligned 16-byte operand chunk.  W0 (columns) and W0^T (rows) are permuted accordingly at pack time.
-// per-CTA scratch: softplus'(z1) unorm16 [64 KB] | h2 planes [P x 64 KB] | 2 x input jacobian (PE [64][128] f32 | grid [96][128] f32)
-constexpr size_t kJRBytes = (size_t)(kPeRows + kMaxGridDim * 3) * 128 * 4;
-__host__ __device__ constexpr size_t kScratchPerCta(int planes) { return 65536 + (size_t)planes * 65536 + 2 * kJRBytes; }
-
-enum { L_G0 = 0, L_G1, L_B1, L_B0, L_C0H, L_C0MISC, L_C1, L_COUNT };
-
-struct TcLayer {
-  unsigned long long w_off;  // byte offset of the packed planes inside the blob
-  int Np;                    // rows of the weight tile (UMMA N); each CTA of a pair holds Np / 2 of them
-  int nkb;                   // K blocks of 32
-};
-
-struct TcArgs {
-  sdfb200_grid_t grid;
-  TcLayer layer[L_COUNT];
-  int use_grid, pe_degree, use_pe, contraction, in_dim, pe_dim, grid_dim, app_dim, use_n_dot_v;
-  int mode;  // 0: sdf only (G0, G1)   1: everything
-  int n_samples, has_bins, n_tiles, n_tile_pairs;
-  long long n_points;
-  float rgb_padding, cos_anneal;
-  const float *origins, *directions, *bins, *appearance, *variance, *beta, *beta_min;
-  const void* table;
-  const char* blob;
-  // fp32 section offsets (bytes)
-  unsigned long long b_g0, b_g1, b_g2, w_g2, b_c0, b_c1, w_c2, b_c2;   // b_c0 = fused bias (bc0 + Wgf b2')
-  char* scratch;
-  unsigned long long scratch_per_cta;
-  sdfb200_field_out_t out;
-  TcRender rnd;
-};
-
 // pack fp32 W (row n, column k at W[rowmap(n)*ldw + colmap(k)]) into bf16 split planes: K-blocked, N split in two halves (one per
 // CTA of a pair), canonical K-major no-swizzle layout inside a half:  [K-block][half][plane][k/8][row in half][8 bf16]
 struct IdxMap { short src[kInK]; };   // packed index -> source index (-1 = zero); identity when unused
-__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int planes, int use_colmap, const IdxMap colmap,
+__global__ void k_tc_pack(const float* __restrict__ W, int ldw, int N, int K, int Np, int nblocks, int kblk, int planes, int use_colmap, const IdxMap colmap,
                           int use_rowmap, const IdxMap rowmap, __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= nblocks * Np * kKB) return;
-  const int kk = idx % kKB;
-  const int n = (idx / kKB) % Np;
-  const int b = idx / (kKB * Np);
-  const int k = b * kKB + kk;
+  if (idx >= nblocks * Np * kblk) return;
+  const int kk = idx % kblk;
+  const int n = (idx / kblk) % Np;
+  const int b = idx / (kblk * Np);
+  const int k = b * kblk + kk;
   const int ks = use_colmap ? (k < kInK ? colmap.src[k] : -1) : (k < K ? k : -1);
   const int ns = use_rowmap ? (n < kInK ? rowmap.src[n] : -1) : (n < N ? n : -1);
   const float w = (ns >= 0 && ks >= 0) ? W[(size_t)ns * ldw + ks] : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
   const int nh = Np / 2, half = n / nh, nl = n - half * nh;
-  const size_t plane_elems = (size_t)nh * kKB;
+  const size_t plane_elems = (size_t)nh * kblk;
   const size_t base = ((size_t)b * 2 + half) * planes * plane_elems;
   const size_t off = (size_t)(kk / 8) * (nh * 8) + (size_t)nl * 8 + (kk % 8);
   out[base + off] = hi;
   if (planes > 1) out[base + plane_elems + off] = lo;
-}
-
-__device__ __forceinline__ uint64_t l2_policy(int kind) {
-  return kind == 1 ? l2_policy_evict_first() : (kind == 2 ? l2_policy_evict_last() : l2_policy_evict_normal());
 }
 
 // colour layer 0 pre-multiplied with the (activation-free) last geo layer: Wc[o][k] = sum_j Wc0[o][33+j] W2[1+j][k],
@@ -120,778 +48,10 @@ __global__ void k_fuse_c0(const float* __restrict__ Wc0, int ldc0, const float* 
   }
 }
 
-// softplus_100 and its derivative through MUFU ex2 / lg2 / rcp.  t = 100 z.  Absolute error ~1e-7 on h (the quantity
-// that feeds the next layer), i.e. at the level of fp32 rounding of the reference's own log1p(exp(.)).
-__device__ __forceinline__ float fast_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float fast_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void softplus100_fast(float z, float& h, float& dsig) {
-  // exp(100 z) = 2^(z * 100 log2 e); log1p(e)/100 = lg2(1+e) * ln2/100.  For small e, 1+e rounds e to ~6e-8 absolute, i.e. an
-  // absolute error of ~4e-10 on h: irrelevant next to the bf16x3 operand rounding (2^-17 relative).
-  const float e = fast_ex2(fminf(z, 0.3f) * 144.26950408889634f);
-  const float u = 1.0f + e;
-  const bool lin = z > 0.2f;                                            // PyTorch's softplus threshold: beta*x > 20
-  h = lin ? z : fast_lg2(u) * 0.006931471805599453f;
-  dsig = lin ? 1.0f : e * fast_rcp(u);
-}
-
-__device__ __forceinline__ void named_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-// sample position of point p (ray r, sample s): o + d * t_start, then SceneContraction (cameras/rays.py:61-73,
-// spatial_distortions.py:66-73).  Also returns the ray direction, the bin start and the bin width.
-struct PointGeom { float px, py, pz, dx, dy, dz, delta, t0, t1; long long ray; };
-__device__ __forceinline__ PointGeom point_geom(const TcArgs& a, long long p) {
-  PointGeom g;
-  g.dx = g.dy = g.dz = 0.f; g.delta = 0.f; g.t0 = g.t1 = 0.f;
-  g.ray = a.has_bins ? p / a.n_samples : p;
-  if (a.has_bins) {
-    const int smp = (int)(p - g.ray * a.n_samples);
-    const float t0 = __ldg(a.bins + g.ray * (a.n_samples + 1) + smp);
-    g.t0 = t0;
-    g.t1 = __ldg(a.bins + g.ray * (a.n_samples + 1) + smp + 1);
-    g.delta = __fsub_rn(g.t1, t0);
-    g.dx = __ldg(a.directions + g.ray * 3); g.dy = __ldg(a.directions + g.ray * 3 + 1); g.dz = __ldg(a.directions + g.ray * 3 + 2);
-    g.px = __fadd_rn(__ldg(a.origins + g.ray * 3 + 0), __fmul_rn(g.dx, t0));
-    g.py = __fadd_rn(__ldg(a.origins + g.ray * 3 + 1), __fmul_rn(g.dy, t0));
-    g.pz = __fadd_rn(__ldg(a.origins + g.ray * 3 + 2), __fmul_rn(g.dz, t0));
-  } else {
-    g.px = __ldg(a.origins + p * 3); g.py = __ldg(a.origins + p * 3 + 1); g.pz = __ldg(a.origins + p * 3 + 2);
-    if (a.directions) { g.dx = __ldg(a.directions + p * 3); g.dy = __ldg(a.directions + p * 3 + 1); g.dz = __ldg(a.directions + p * 3 + 2); }
-  }
-  if (a.contraction != SDFB200_CONTRACT_NONE) {
-    const float mag = a.contraction == SDFB200_CONTRACT_LINF
-                          ? fmaxf(fabsf(g.px), fmaxf(fabsf(g.py), fabsf(g.pz)))
-                          : sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(g.px, g.px), __fmul_rn(g.py, g.py)), __fmul_rn(g.pz, g.pz)));
-    if (mag >= 1.f) {
-      const float k = __fsub_rn(2.f, __fdiv_rn(1.f, mag));
-      g.px = __fmul_rn(k, __fdiv_rn(g.px, mag)); g.py = __fmul_rn(k, __fdiv_rn(g.py, mag)); g.pz = __fmul_rn(k, __fdiv_rn(g.pz, mag));
-    }
-  }
-  return g;
-}
-
-// one 16-byte chunk (8 consecutive K columns of one row) of a small-K smem operand, all planes: layout [plane][k/8][row][8]
-template <int P>
-__device__ __forceinline__ void store_chunk(uint8_t* inA, int row, int chunk, const float (&v)[8]) {
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int e = 0; e < 4; ++e) split2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-  *reinterpret_cast<uint4*>(inA + (size_t)chunk * 2048 + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  if (P > 1) *reinterpret_cast<uint4*>(inA + (kInK / 8) * 2048 + (size_t)chunk * 2048 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-// Geo input of one tile, one thread per point (gather warps): hash levels in groups of four (= one operand chunk), PE, x.
-// Outputs: the smem operand (bf16 planes, kernel column order) and, in the per-CTA global scratch, the per-point input
-// jacobian: PE [i][row] (d PE_i / d x_axis(i)) and grid [(col*3 + d)][row] (with the 1/4 of (x+2)/4 folded in).
-template <int P>
-__device__ __forceinline__ void encode_tile(const TcArgs& a, int tile, int row, uint8_t* inA, uint8_t* enc, uint64_t pol_table) {
-  float* Jpe = reinterpret_cast<float*>(enc);
-  float* Jg = Jpe + kPeRows * 128;
-  const long long p_raw = (long long)tile * 128 + row;
-  const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
-  const PointGeom g = point_geom(a, p);
-  const float x01 = (g.px + 2.0f) * 0.25f, y01 = (g.py + 2.0f) * 0.25f, z01 = (g.pz + 2.0f) * 0.25f;   // sdf_field.py:384
-  // ---- hash grid: chunks 0..3 ----
-#pragma unroll 1
-  for (int ch = 0; ch < 4; ++ch) {
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int l = ch * 4 + j;
-      float o[2] = {0.f, 0.f};
-      float dj[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
-      if (a.use_grid && l < a.grid.n_levels && l < a.grid.active_levels) {
-        if (a.grid.table_dtype == SDFB200_DT_F16) encode_level<__half, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, pol_table);
-        else encode_level<float, 2, true, true>(a.grid, a.table, l, x01, y01, z01, o, dj, pol_table);
-      }
-      v[2 * j] = o[0]; v[2 * j + 1] = o[1];
-      if (a.mode != 0 && l < a.grid.n_levels) {
-#pragma unroll
-        for (int f = 0; f < 2; ++f) {
-          const int cg = l * 2 + f;
-          Jg[(cg * 3 + 0) * 128 + row] = 0.25f * dj[f][0];
-          Jg[(cg * 3 + 1) * 128 + row] = 0.25f * dj[f][1];
-          Jg[(cg * 3 + 2) * 128 + row] = 0.25f * dj[f][2];
-        }
-      }
-    }
-    store_chunk<P>(inA, row, ch, v);
-  }
-  // ---- PE | x | zero padding: chunks 4..11.  Kernel column 32 + i holds PE_i, 32 + pe_dim + j holds x_j ----
-  const int deg = a.pe_degree, half = 3 * deg;
-  const float pc[3] = {g.px, g.py, g.pz};
-#pragma unroll 1
-  for (int ch = 4; ch < kInK / 8; ++ch) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int i = ch * 8 + e - 32;
-      float val = 0.f;
-      if (i < a.pe_dim) {                                   // sin(x 2^k) | sin(x 2^k + pi/2)   (encodings.py:194-198)
-        const int ia = i >= half ? i - half : i;
-        const int b = ia / deg, k = ia - b * deg;
-        const float fr = (float)(1 << k);
-        const float arg = i >= half ? pc[b] * fr + kHalfPiF : pc[b] * fr;
-        float s, c;
-        sincosf(arg, &s, &c);
-        val = a.use_pe ? s : 0.f;
-        // autograd of sin on the forward's own fp32 arguments: d/dx_b = 2^k cos(arg)
-        if (a.mode != 0) Jpe[i * 128 + row] = a.use_pe ? fr * c : 0.f;
-      } else if (i < a.pe_dim + 3) {
-        val = pc[i - a.pe_dim];
-      }
-      v[e] = val;
-    }
-    store_chunk<P>(inA, row, ch, v);
-  }
-}
-
-// static colour-operand columns of a tile (kernel columns 8..95 = chunks 1..11): x(3) | dir-enc(24) | dir(3) | appearance | 0,
-// written IN PLACE over the tile's geo input once G0 has consumed it (chunk 0 = [grad, n.v] comes from the epilogue warps)
-template <int P>
-__device__ __forceinline__ void colour_static_tile(const TcArgs& a, int tile, int row, uint8_t* inA) {
-  const long long p_raw = (long long)tile * 128 + row;
-  const long long p = p_raw < a.n_points ? p_raw : a.n_points - 1;
-  const PointGeom g = point_geom(a, p);
-  const float pc[3] = {g.px, g.py, g.pz};
-  const float dd[3] = {g.dx, g.dy, g.dz};
-#pragma unroll 1
-  for (int ch = 0; ch < 11; ++ch) {
-    float v[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j = ch * 8 + e;
-      float val = 0.f;
-      if (j < 3) val = pc[j];
-      else if (j < 15) { const int i = j - 3; val = sinf(dd[i >> 2] * (float)(1 << (i & 3))); }
-      else if (j < 27) { const int i = j - 15; val = sinf(dd[i >> 2] * (float)(1 << (i & 3)) + kHalfPiF); }
-      else if (j < 30) val = dd[j - 27];
-      else if (j < 30 + a.app_dim) val = a.appearance ? __ldg(a.appearance + g.ray * a.app_dim + (j - 30)) : 0.f;
-      v[e] = val;
-    }
-    store_chunk<P>(inA, row, 1 + ch, v);
-  }
-}
-
-#ifdef SDFB200_TC_TIMING
-__device__ long long g_tc_timing[16 * 32];
-#define TC_STAMP(k)                                                                                                  \
-  do {                                                                                                               \
-    if (blockIdx.x == 0 && tid == 0 && tile_no < 16) g_tc_timing[tile_no * 32 + (k)] = clock64();                   \
-  } while (0)
-#else
-#define TC_STAMP(k) do { } while (0)
-#endif
-
-template <int P>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_field_tc(const __grid_constant__ TcArgs a) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  constexpr uint32_t kInBytes = (uint32_t)P * (kInK / 8) * 2048;       // small-K operand (all planes), double buffered
-  constexpr uint32_t kStageBytes = (uint32_t)P * 128 * kKB * 2;        // this CTA's half of one weight K-block, all planes
-  uint8_t* inA0 = smem;
-  uint8_t* ring = smem + 2 * kInBytes;
-  float* fbuf = reinterpret_cast<float*>(ring + kStages * kStageBytes);
-  float* red = fbuf;                  // [3][2][128] partial sums
-  float* prm = fbuf + 6 * 128;        // [9][256] biases / fp32 weight rows used by the epilogues
-  float* racc = prm + 9 * 256;        // [8][4] per-ray accumulators of the fused compositing (rays spanning several warps)
-  float* lastrgb = racc + 32;         // [4][3]
-  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_ready, in_ready, misc_ready;
-  __shared__ double wtot[4];
-  __shared__ uint32_t tmem_base_s;
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_ctarank();
-  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
-  if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&peer_full[s], 1); }
-    mbar_init(&dfull, 1);
-    mbar_init(&g0done, 1);
-    mbar_init(&a_ready, 2 * kEpiWarps);
-    mbar_init(&in_ready, 2 * kGatherWarps);
-    mbar_init(&misc_ready, 2 * kGatherWarps);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc2<512>(&tmem_base_s);
-  {
-    const char* blob = a.blob;
-    const float* src[9] = {reinterpret_cast<const float*>(blob + a.b_g0), reinterpret_cast<const float*>(blob + a.b_g1),
-                           reinterpret_cast<const float*>(blob + a.b_g1), reinterpret_cast<const float*>(blob + a.w_g2),
-                           reinterpret_cast<const float*>(blob + a.b_c0), reinterpret_cast<const float*>(blob + a.b_c1),
-                           reinterpret_cast<const float*>(blob + a.w_c2), reinterpret_cast<const float*>(blob + a.w_c2) + 256,
-                           reinterpret_cast<const float*>(blob + a.w_c2) + 512};
-    for (int i = tid; i < 9 * 256; i += kTcThreads) prm[i] = src[i >> 8][i & 255];
-    if (tid < 44) racc[tid] = 0.f;
-  }
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t d_tmem = tmem;          // accumulator: columns [0,256)
-  const uint32_t a_tmem = tmem + 256;    // A planes: plane p at columns 256 + 128 p
-  const int nphase_layers = a.mode == 0 ? 2 : L_COUNT;
-  // leader-side barriers that both CTAs arrive on
-  const uint32_t a_ready_r = mapa_shared(smem_u32(&a_ready), 0);
-  const uint32_t in_ready_r = mapa_shared(smem_u32(&in_ready), 0);
-  const uint32_t misc_ready_r = mapa_shared(smem_u32(&misc_ready), 0);
-
-  if (warp == kWarpProducer) {
-    // ============================== weight producer (this CTA's half of every weight tile) ==============================
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
-        for (int L = 0; L < nphase_layers; ++L) {
-          const TcLayer ly = a.layer[L];
-          const uint32_t bytes = (uint32_t)P * (ly.Np / 2) * kKB * 2;
-          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.blob) + ly.w_off + (size_t)rank * bytes;
-          for (int kb = 0; kb < ly.nkb; ++kb, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&empty[s], ((it / kStages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&full[s], bytes);
-            bulk_g2s(ring + (size_t)s * kStageBytes, src + (size_t)kb * 2 * bytes, bytes, &full[s]);
-          }
-        }
-      }
-    }
-  } else if (warp == kWarpMma) {
-    if (rank != 0) {
-      // ============================== peer CTA: forward "my half of stage s has landed" to the leader ==============================
-      if (lane == 0) {
-        uint32_t it = 0;
-        for (int tp = pair; tp < a.n_tile_pairs; tp += npairs)
-          for (int L = 0; L < nphase_layers; ++L)
-            for (int kb = 0; kb < a.layer[L].nkb; ++kb, ++it) {
-              const int s = it % kStages;
-              mbar_wait(&full[s], (it / kStages) & 1);
-              mbar_arrive_remote(mapa_shared(smem_u32(&peer_full[s]), 0));
-            }
-      }
-    } else if (lane == 0) {
-      // ============================== MMA issuer (leader CTA, one thread) ==============================
-      uint32_t it = 0, par_a = 0, par_in = 0, par_misc = 0;
-      int tile_no = -1;
-      for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
-        ++tile_no;
-        const uint32_t in_base = smem_u32(inA0 + (tile_no & 1) * kInBytes);
-        for (int L = 0; L < nphase_layers; ++L) {
-          if (L == L_C0MISC) {                                   // accumulates onto C0H; its static columns come from the gather warps
-            mbar_wait_cluster(&misc_ready, par_misc); par_misc ^= 1;
-          } else {
-            mbar_wait_cluster(&a_ready, par_a); par_a ^= 1;     // both CTAs: A operand of this layer staged, D drained
-            if (L == L_G0) { mbar_wait_cluster(&in_ready, par_in); par_in ^= 1; }
-          }
-          tc_fence_after();
-          const TcLayer ly = a.layer[L];
-          const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
-          const uint32_t idesc = make_idesc_bf16(256, ly.Np);
-          const uint32_t lbo_b = (uint32_t)(ly.Np / 2) * 16, plane_b = (uint32_t)(ly.Np / 2) * kKB * 2;
-          uint32_t acc = (L == L_C0MISC) ? 1u : 0u;
-          for (int kb = 0; kb < ly.nkb; ++kb, ++it) {
-            const int s = it % kStages;
-            mbar_wait(&full[s], (it / kStages) & 1);
-            mbar_wait_cluster(&peer_full[s], (it / kStages) & 1);
-            tc_fence_after();
-            const uint32_t wbase = smem_u32(ring + (size_t)s * kStageBytes);
-#pragma unroll
-            for (int j = 0; j < kKB / 16; ++j) {
-              const int kstep = kb * (kKB / 16) + j;
-              const uint64_t b0 = make_smem_desc(wbase + j * 2 * lbo_b, lbo_b, 128);
-              const uint64_t b1 = make_smem_desc(wbase + plane_b + j * 2 * lbo_b, lbo_b, 128);
-              if (a_in_smem) {
-                const uint64_t a0 = make_smem_desc(in_base + kstep * 2 * 2048, 2048, 128);
-                mma_ss2(d_tmem, a0, b0, idesc, acc);
-                acc = 1;
-                if (P > 1) {
-                  const uint64_t a1 = make_smem_desc(in_base + (kInK / 8) * 2048 + kstep * 2 * 2048, 2048, 128);
-                  mma_ss2(d_tmem, a1, b0, idesc, 1);
-                  mma_ss2(d_tmem, a0, b1, idesc, 1);
-                }
-              } else {
-                mma_ts2(d_tmem, a_tmem + kstep * 8, b0, idesc, acc);
-                acc = 1;
-                if (P > 1) {
-                  mma_ts2(d_tmem, a_tmem + 128 + kstep * 8, b0, idesc, 1);
-                  mma_ts2(d_tmem, a_tmem + kstep * 8, b1, idesc, 1);
-                }
-              }
-            }
-            mma_commit2(&empty[s]);
-          }
-          if (L == L_G0) mma_commit2(&g0done);               // the geo input of this tile has been consumed (gather warps)
-          if (L != L_C0H) mma_commit2(&dfull);               // C0H is completed by C0MISC
-        }
-      }
-    }
-  } else if (warp >= kEpiWarps) {
-    // ============================== gather / encode warps: one thread per point, one tile ahead ==============================
-    const int row = (warp - kEpiWarps) * 32 + lane;
-    uint8_t* enc_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta) + 65536 + (size_t)P * 65536;
-    const uint64_t pol_table = l2_policy_evict_last();
-    int tile_no = -1;
-    {
-      const int tile0 = 2 * pair + (int)rank;
-      encode_tile<P>(a, tile0, row, inA0, enc_s, pol_table);
-      fence_async_smem();
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(in_ready_r);
-    }
-    for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
-      ++tile_no;
-      const int tile = 2 * tp + (int)rank;
-      const int buf = tile_no & 1;
-      mbar_wait_backoff(&g0done, tile_no & 1);              // G0 of this tile is complete (hence every MMA of the previous tile)
-      if (a.mode != 0) {
-        colour_static_tile<P>(a, tile, row, inA0 + buf * kInBytes);
-        fence_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(misc_ready_r);
-      }
-      if (tp + npairs < a.n_tile_pairs) {
-        encode_tile<P>(a, tile + 2 * npairs, row, inA0 + (buf ^ 1) * kInBytes, enc_s + (size_t)(buf ^ 1) * kJRBytes, pol_table);
-        fence_async_smem();
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive_remote(in_ready_r);
-      }
-    }
-  } else {
-    // ============================== epilogue warps (8): thread (row, q) owns accumulator columns [128 q, 128 q + 128) ==============================
-    const int wq = warp & 3;                              // TMEM lane quadrant
-    const int row = wq * 32 + lane;                       // tile row == TMEM lane
-    const int q = warp >> 2;                              // column half
-    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    const char* blob = a.blob;
-    const float* p_bg0 = prm;             // smem copies (broadcast LDS.128 instead of one LDG per element)
-    const float* p_bg1 = prm + 256;
-    const float* p_wg2 = prm + 768;       // row 0 of the last geo layer
-    const float* p_bc0 = prm + 1024;
-    const float* p_bc1 = prm + 1280;
-    const float* p_wc2 = prm + 1536;      // [3][256]
-    const float sdf_bias = __ldg(reinterpret_cast<const float*>(blob + a.b_g2));
-    const float* b_c2 = reinterpret_cast<const float*>(blob + a.b_c2);
-    uint8_t* sig_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta);   // [32 units][128 rows][16 B]
-    uint8_t* gf_s = sig_s + 65536;                                                                      // [P][32 units][128][16 B]
-    uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x input jacobian
-    uint32_t dpar = 0;
-    const uint64_t pol_stream = l2_policy_evict_first();
-    const uint64_t pol_keep = l2_policy_evict_normal();
-    auto epi_arrive = [&]() {
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(a_ready_r);
-    };
-
-    int tile_no = -1;
-    for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
-      ++tile_no;
-      const int tile = 2 * tp + (int)rank;
-      TC_STAMP(0);
-      const int buf = tile_no & 1;
-      uint8_t* inA = inA0 + buf * kInBytes;               // geo input now, colour operand later
-      const uint8_t* enc_cur = enc_s + (size_t)buf * kJRBytes;
-      const long long p_raw = (long long)tile * 128 + row;
-      const bool valid = p_raw < a.n_points;
-      const long long p = valid ? p_raw : a.n_points - 1;
-      const PointGeom pg = point_geom(a, p);
-      const float px = pg.px, py = pg.py, pz = pg.pz, dirx = pg.dx, diry = pg.dy, dirz = pg.dz, delta = pg.delta;
-      if (q == 0 && valid) {
-        if (a.out.points_norm) a.out.points_norm[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
-        if (a.out.points) { a.out.points[p * 3] = px; a.out.points[p * 3 + 1] = py; a.out.points[p * 3 + 2] = pz; }
-      }
-      epi_arrive();                                        // D and the A planes are free (previous tile fully drained)
-      TC_STAMP(1);
-
-      // ---------------- E0: h1 = softplus(z1) -> A planes ; softplus'(z1) -> scratch ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(2);
-#pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
-        uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-        float sg[16];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p_bg0 + col0 + j);
-          float h0, h1, h2, h3;
-          softplus100_fast(__uint_as_float(v[j]) + b4.x, h0, sg[j]);
-          softplus100_fast(__uint_as_float(v[j + 1]) + b4.y, h1, sg[j + 1]);
-          softplus100_fast(__uint_as_float(v[j + 2]) + b4.z, h2, sg[j + 2]);
-          softplus100_fast(__uint_as_float(v[j + 3]) + b4.w, h3, sg[j + 3]);
-          split2(h0, h1, hi[j >> 1], lo[j >> 1]);
-          split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
-        }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
-        if (a.mode != 0) {
-#pragma unroll
-          for (int u8 = 0; u8 < 2; ++u8) {
-            // 8 values -> 8 x unorm16 (one 16-byte unit per thread): absolute error 2^-17
-            uint32_t pk[4];
-#pragma unroll
-            for (int e2 = 0; e2 < 4; ++e2) {
-              const uint32_t lo16 = __float2uint_rn(sg[u8 * 8 + 2 * e2] * 65535.0f), hi16 = __float2uint_rn(sg[u8 * 8 + 2 * e2 + 1] * 65535.0f);
-              pk[e2] = lo16 | (hi16 << 16);
-            }
-            st_stream(sig_s + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, make_uint4(pk[0], pk[1], pk[2], pk[3]), pol_stream);
-          }
-        }
-      }
-      tc_wait_st();
-      epi_arrive();
-      TC_STAMP(3);
-
-      // ---------------- E1: h2 -> scratch planes (colour layer 0 input) ; sdf = W2[0,:] . h2 + b (fp32) ;
-      //                      g2 = W2[0,:] * softplus'(z2) -> A planes (seed of the reverse sweep)
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(4);
-      float sdf_part = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
-        uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8], ghi[8], glo[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(p_bg1 + col0 + j);
-          const float4 w4 = *reinterpret_cast<const float4*>(p_wg2 + col0 + j);
-          float h0, h1, h2, h3, s0, s1, s2, s3;
-          softplus100_fast(__uint_as_float(v[j]) + b4.x, h0, s0);
-          softplus100_fast(__uint_as_float(v[j + 1]) + b4.y, h1, s1);
-          softplus100_fast(__uint_as_float(v[j + 2]) + b4.z, h2, s2);
-          softplus100_fast(__uint_as_float(v[j + 3]) + b4.w, h3, s3);
-          sdf_part = fmaf(w4.x, h0, sdf_part); sdf_part = fmaf(w4.y, h1, sdf_part);
-          sdf_part = fmaf(w4.z, h2, sdf_part); sdf_part = fmaf(w4.w, h3, sdf_part);
-          split2(h0, h1, hi[j >> 1], lo[j >> 1]);
-          split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
-          if (a.mode != 0) {
-            split2(w4.x * s0, w4.y * s1, ghi[j >> 1], glo[j >> 1]);
-            split2(w4.z * s2, w4.w * s3, ghi[(j >> 1) + 1], glo[(j >> 1) + 1]);
-          }
-        }
-        if (a.mode != 0) {
-#pragma unroll
-          for (int u8 = 0; u8 < 2; ++u8) {
-            const size_t unit = ((size_t)((col0 >> 3) + u8) * 128 + row) * 16;
-            st_stream(gf_s + unit, make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]), pol_stream);
-            if (P > 1) st_stream(gf_s + 65536 + unit, make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]), pol_stream);
-          }
-          tmem_st8(a_tmem + lane_addr + (col0 >> 1), ghi);
-          if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), glo);
-        }
-      }
-      tc_wait_st();
-      red[q * 128 + row] = sdf_part;
-      if (a.mode != 0) epi_arrive(); else tc_fence_before();
-      TC_STAMP(5);
-      named_sync(2, kEpiThreads);
-      const float sdf = (red[row] + red[128 + row]) + sdf_bias;
-      if (q == 0 && valid && a.out.sdf) a.out.sdf[p] = sdf;
-      if (a.mode == 0) {
-        named_sync(2, kEpiThreads);  // `red` is reused by the next tile
-        continue;
-      }
-
-      // ---------------- EB1: g1 = (W1^T g2) * softplus'(z1) -> A planes ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(8);
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
-        uint4 sp[2];
-#pragma unroll
-        for (int u8 = 0; u8 < 2; ++u8) sp[u8] = ld_stream_u4(sig_s + ((size_t)((col0 >> 3) + u8) * 128 + row) * 16, pol_stream);
-        uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-        const uint32_t spw[8] = {sp[0].x, sp[0].y, sp[0].z, sp[0].w, sp[1].x, sp[1].y, sp[1].z, sp[1].w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float s0 = (float)(spw[j] & 0xFFFFu) * (1.0f / 65535.0f), s1 = (float)(spw[j] >> 16) * (1.0f / 65535.0f);
-          split2(__uint_as_float(v[2 * j]) * s0, __uint_as_float(v[2 * j + 1]) * s1, hi[j], lo[j]);
-        }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
-      }
-      tc_wait_st();
-      epi_arrive();
-      TC_STAMP(9);
-
-      // ---------------- EB0: gin (96 cols, kernel order) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ;
-      //                       h2 planes back into the A operand for colour layer 0
-      // thread (row, q) owns the operand chunks {0,1,4,5,8} (q = 0) / {2,3,6,7} (q = 1): two grid chunks + its share of PE / x
-      // (chunks 9..11 are zero padding).  The jacobian does not depend on this phase's MMA: the first chunk is fetched before the wait.
-      const float* Jpe = reinterpret_cast<const float*>(enc_cur);
-      const float* Jg = Jpe + kPeRows * 128;
-      const int deg = a.pe_degree, half = 3 * deg;
-      float gx = 0.f, gy = 0.f, gz = 0.f;
-#pragma unroll 1
-      for (int ci = 0; ci < 5; ++ci) {
-        const int ck = ci < 2 ? 2 * q + ci : (ci < 4 ? 4 + 2 * q + (ci - 2) : (q == 0 ? 8 : -1));
-        if (ck >= 0) {
-          float jx[8], jy[8], jz[8];
-          if (ck < 4) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int cg = ck * 8 + j;
-              const bool on = cg < a.grid_dim;
-              jx[j] = on ? ld_stream_f1(Jg + (cg * 3 + 0) * 128 + row, pol_keep) : 0.f;
-              jy[j] = on ? ld_stream_f1(Jg + (cg * 3 + 1) * 128 + row, pol_keep) : 0.f;
-              jz[j] = on ? ld_stream_f1(Jg + (cg * 3 + 2) * 128 + row, pol_keep) : 0.f;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const int i = ck * 8 + j - 32;
-              const bool is_pe = i < a.pe_dim;
-              const int ia = i >= half ? i - half : i;                       // axis block of a PE column
-              const int xj = i - a.pe_dim;                                   // 0..2: the x columns
-              const float dv = is_pe ? ld_stream_f1(Jpe + i * 128 + row, pol_keep) : 0.f;
-              jx[j] = is_pe ? (ia < deg ? dv : 0.f) : (xj == 0 ? 1.f : 0.f);
-              jy[j] = is_pe ? ((ia >= deg && ia < 2 * deg) ? dv : 0.f) : (xj == 1 ? 1.f : 0.f);
-              jz[j] = is_pe ? (ia >= 2 * deg ? dv : 0.f) : (xj == 2 ? 1.f : 0.f);
-            }
-          }
-          if (ci == 0) {
-            mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-            TC_STAMP(10);
-          }
-          uint32_t gin_v[8];
-          tmem_ld8(d_tmem + lane_addr + ck * 8, gin_v);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float g = __uint_as_float(gin_v[j]);
-            gx = fmaf(g, jx[j], gx); gy = fmaf(g, jy[j], gy); gz = fmaf(g, jz[j], gz);
-          }
-        }
-      }
-      red[(0 * 2 + q) * 128 + row] = gx; red[(1 * 2 + q) * 128 + row] = gy; red[(2 * 2 + q) * 128 + row] = gz;
-      // h2 planes back into the A operand for colour layer 0 (two batches of 8 units: all L2 loads of a batch in flight together)
-#pragma unroll 1
-      for (int hb = 0; hb < 2; ++hb) {
-        uint4 gh[8], gl[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const size_t unit = ((size_t)(q * 16 + hb * 8 + u) * 128 + row) * 16;
-          gh[u] = ld_stream_u4(gf_s + unit, pol_stream);
-          if (P > 1) gl[u] = ld_stream_u4(gf_s + 65536 + unit, pol_stream);
-        }
-#pragma unroll
-        for (int u = 0; u < 8; u += 2) {
-          const uint32_t h8[8] = {gh[u].x, gh[u].y, gh[u].z, gh[u].w, gh[u + 1].x, gh[u + 1].y, gh[u + 1].z, gh[u + 1].w};
-          tmem_st8(a_tmem + lane_addr + (q * 16 + hb * 8 + u) * 4, h8);
-          if (P > 1) {
-            const uint32_t l8[8] = {gl[u].x, gl[u].y, gl[u].z, gl[u].w, gl[u + 1].x, gl[u + 1].y, gl[u + 1].z, gl[u + 1].w};
-            tmem_st8(a_tmem + 128 + lane_addr + (q * 16 + hb * 8 + u) * 4, l8);
-          }
-        }
-      }
-      named_sync(2, kEpiThreads);
-      const float grx = red[(0 * 2 + 0) * 128 + row] + red[(0 * 2 + 1) * 128 + row];
-      const float gry = red[(1 * 2 + 0) * 128 + row] + red[(1 * 2 + 1) * 128 + row];
-      const float grz = red[(2 * 2 + 0) * 128 + row] + red[(2 * 2 + 1) * 128 + row];
-      const float gn = fmaxf(sqrtf(grx * grx + gry * gry + grz * grz), 1e-12f);      // F.normalize eps
-      const float nx = grx / gn, ny = gry / gn, nz = grz / gn;
-      if (q == 0) {
-        // chunk 0 of the colour operand: [grad(3), n.v, 0, 0, 0, 0]   (sdf_field.py:572-584; columns re-ordered at pack time)
-        const float c0v[8] = {grx, gry, grz, a.use_n_dot_v ? nx * dirx + ny * diry + nz * dirz : 0.f, 0.f, 0.f, 0.f, 0.f};
-        store_chunk<P>(inA, row, 0, c0v);
-      }
-      tc_wait_st();
-      fence_async_smem();
-      epi_arrive();
-      TC_STAMP(11);
-
-      // ---------------- EC0: relu -> A planes ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(12);
-#pragma unroll 2
-      for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
-        uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
-        tc_wait_ld();
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float2 b2 = *reinterpret_cast<const float2*>(p_bc0 + col0 + j);
-          split2(fmaxf(__uint_as_float(v[j]) + b2.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b2.y, 0.f), hi[j >> 1], lo[j >> 1]);
-        }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
-      }
-      tc_wait_st();
-      epi_arrive();
-      TC_STAMP(13);
-
-      // ---------------- EC1: relu, last colour layer (256 -> 3) as fp32 dots ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
-      TC_STAMP(14);
-      {
-        float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 2
-        for (int cc = 0; cc < 8; ++cc) {
-          const int col0 = q * 128 + cc * 16;
-          uint32_t v[16];
-          tmem_ld16(d_tmem + lane_addr + col0, v);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float c1 = fmaxf(__uint_as_float(v[j]) + p_bc1[col0 + j], 0.f);
-            r0 = fmaf(p_wc2[col0 + j], c1, r0);
-            r1 = fmaf(p_wc2[256 + col0 + j], c1, r1);
-            r2 = fmaf(p_wc2[512 + col0 + j], c1, r2);
-          }
-        }
-        named_sync(2, kEpiThreads);   // everyone has consumed the gradient partials in `red`
-        red[(0 * 2 + q) * 128 + row] = r0; red[(1 * 2 + q) * 128 + row] = r1; red[(2 * 2 + q) * 128 + row] = r2;
-      }
-      tc_fence_before();
-      named_sync(2, kEpiThreads);
-      if (q == 0) {
-        // ---------------- per-point heads ----------------
-        float rgbv[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float raw = (red[(c * 2 + 0) * 128 + row] + red[(c * 2 + 1) * 128 + row]) + __ldg(b_c2 + c);
-          rgbv[c] = sigmoidf_(raw) * (1.f + 2.f * a.rgb_padding) - a.rgb_padding;
-        }
-        float density = 0.f, alpha = 0.f;
-        if (a.out.density || (a.rnd.enabled && a.rnd.from_density)) {
-          const float beta = fabsf(__ldg(a.beta)) + __ldg(a.beta_min);
-          const float sg = sdf > 0.f ? 1.f : (sdf < 0.f ? -1.f : 0.f);
-          density = (1.0f / beta) * (0.5f + 0.5f * sg * expm1f(-fabsf(sdf) / beta));
-        }
-        if (a.out.alpha || (a.rnd.enabled && !a.rnd.from_density)) {
-          const float inv_s = fminf(fmaxf(expf(__ldg(a.variance) * 10.0f), 1e-6f), 1e6f);
-          const float true_cos = dirx * grx + diry * gry + dirz * grz;
-          const float iter_cos = -(fmaxf(-true_cos * 0.5f + 0.5f, 0.f) * (1.0f - a.cos_anneal) + fmaxf(-true_cos, 0.f) * a.cos_anneal);
-          const float prev_cdf = sigmoidf_((sdf - iter_cos * delta * 0.5f) * inv_s), next_cdf = sigmoidf_((sdf + iter_cos * delta * 0.5f) * inv_s);
-          alpha = fminf(fmaxf((prev_cdf - next_cdf + 1e-5f) / (prev_cdf + 1e-5f), 0.f), 1.f);
-        }
-        if (valid) {
-          if (a.out.rgb) { a.out.rgb[p * 3] = rgbv[0]; a.out.rgb[p * 3 + 1] = rgbv[1]; a.out.rgb[p * 3 + 2] = rgbv[2]; }
-          if (a.out.gradients) { a.out.gradients[p * 3] = grx; a.out.gradients[p * 3 + 1] = gry; a.out.gradients[p * 3 + 2] = grz; }
-          if (a.out.normals) { a.out.normals[p * 3] = nx; a.out.normals[p * 3 + 1] = ny; a.out.normals[p * 3 + 2] = nz; }
-          if (a.out.density) a.out.density[p] = density;
-          if (a.out.occupancy) a.out.occupancy[p] = sigmoidf_(-10.0f * sdf);
-          if (a.out.alpha) a.out.alpha[p] = alpha;
-        }
-        if (a.rnd.enabled) {
-          // ---------------- fused compositing: the tile holds 128 / S whole rays; row -> (ray, sample) = (row / S, row % S) ----------------
-          const int S = a.n_samples;
-          const int s_idx = row % S;
-          const int rl = row / S;                                   // ray within the tile
-          const bool dens = a.rnd.from_density != 0;
-          // factor by which the transmittance drops across this sample: 1 - alpha + 1e-7 (rays.py:204-206), or as an exponent
-          // delta * sigma for the density form (rays.py:160-170)
-          const float dd = valid ? __fmul_rn(delta, density) : 0.f;
-          double f = dens ? (double)dd : (valid ? (double)__fadd_rn(__fsub_rn(1.0f, alpha), 1e-7f) : 1.0);
-          double incl = f;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            const double o = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d && s_idx >= d) incl = dens ? incl + o : incl * o;
-          }
-          double excl = __shfl_up_sync(0xffffffffu, incl, 1);
-          if (lane == 0 || s_idx == 0) excl = dens ? 0.0 : 1.0;
-          if (lane == 31) wtot[wq] = incl;
-          named_sync(3, 128);
-          if (S > 32) {
-            const int first = (wq * 32 / S) * (S / 32);
-            for (int w2 = first; w2 < wq; ++w2) excl = dens ? excl + wtot[w2] : excl * wtot[w2];
-          }
-          const float T = dens ? expf(-(float)excl) : (float)excl;
-          const float al = dens ? __fsub_rn(1.0f, expf(-dd)) : alpha;
-          const float w = valid ? __fmul_rn(al, T) : 0.f;
-          const float mid = __fdiv_rn(__fadd_rn(pg.t0, pg.t1), 2.0f);            // (starts + ends) / 2, renderers.py:247
-          if (valid && a.rnd.weights) a.rnd.weights[p] = w;
-          float vs[8] = {w, w * rgbv[0], w * rgbv[1], w * rgbv[2], w * nx, w * ny, w * nz, w * mid};
-          float smin = valid ? mid : INFINITY, smax = valid ? mid : -INFINITY;
-          const int span = S < 32 ? S : 32;
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            if (d < span) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) vs[k] += __shfl_down_sync(0xffffffffu, vs[k], d);
-            }
-            smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, d));
-            smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, d));
-          }
-          if (a.rnd.steps_minmax && lane == 0 && smin <= smax) { atomic_min_float(a.rnd.steps_minmax, smin); atomic_max_float(a.rnd.steps_minmax + 1, smax); }
-          if (S > 32) {
-            if (lane == 0) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) atomicAdd(&racc[k * 4 + rl], vs[k]);
-            }
-            if (s_idx == S - 1) { lastrgb[rl * 3] = rgbv[0]; lastrgb[rl * 3 + 1] = rgbv[1]; lastrgb[rl * 3 + 2] = rgbv[2]; }
-            named_sync(3, 128);
-            if (s_idx == 0) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k) { vs[k] = racc[k * 4 + rl]; racc[k * 4 + rl] = 0.f; }
-            }
-          }
-          // transmittance after the last sample (alphas: transmittance[:, -1] = bg_transmittance, neus.py:101) / before it (densities: volsdf.py:67-68)
-          double tot;
-          float lr, lg, lb;
-          if (S > 32) {
-            const int first = (wq * 32 / S) * (S / 32);
-            tot = dens ? 0.0 : 1.0;
-            const int nw = dens ? S / 32 - 1 : S / 32;
-            for (int w2 = first; w2 < first + nw; ++w2) tot = dens ? tot + wtot[w2] : tot * wtot[w2];
-            lr = lastrgb[rl * 3]; lg = lastrgb[rl * 3 + 1]; lb = lastrgb[rl * 3 + 2];
-          } else {
-            const int last = (lane - s_idx) + S - 1;
-            tot = __shfl_sync(0xffffffffu, dens ? excl : incl, last);
-            lr = __shfl_sync(0xffffffffu, rgbv[0], last); lg = __shfl_sync(0xffffffffu, rgbv[1], last); lb = __shfl_sync(0xffffffffu, rgbv[2], last);
-          }
-          if (S > 32 && dens) {
-            // exclusive sum at the last sample of the ray = transmittance exponent before the last sample; it lives in the last warp of the ray
-            if (s_idx == S - 1) wtot[wq] = excl;       // (wtot of the ray's last warp is no longer needed by anyone else)
-            named_sync(3, 128);
-            tot = wtot[(wq * 32 / S) * (S / 32) + S / 32 - 1];
-          }
-          const long long ray = (long long)tile * (128 / S) + rl;
-          if (s_idx == 0 && ray * S < a.n_points) {
-            const float acc = vs[0];
-            if (a.rnd.rgb) {
-              float bgc[3] = {0.f, 0.f, 0.f};
-              if (a.rnd.bg_mode == SDFB200_BG_COLOR) { bgc[0] = a.rnd.bg[0]; bgc[1] = a.rnd.bg[1]; bgc[2] = a.rnd.bg[2]; }
-              else if (a.rnd.bg_mode == SDFB200_BG_PER_RAY) { bgc[0] = a.rnd.bg[ray * 3]; bgc[1] = a.rnd.bg[ray * 3 + 1]; bgc[2] = a.rnd.bg[ray * 3 + 2]; }
-              else { bgc[0] = lr; bgc[1] = lg; bgc[2] = lb; }
-              const float rem = 1.0f - acc;
-              const float o[3] = {vs[1] + bgc[0] * rem, vs[2] + bgc[1] * rem, vs[3] + bgc[2] * rem};
-#pragma unroll
-              for (int c = 0; c < 3; ++c) a.rnd.rgb[ray * 3 + c] = a.rnd.clamp01 ? fminf(fmaxf(o[c], 0.f), 1.f) : o[c];
-            }
-            if (a.rnd.accumulation) a.rnd.accumulation[ray] = acc;
-            if (a.rnd.normal) { a.rnd.normal[ray * 3] = vs[4]; a.rnd.normal[ray * 3 + 1] = vs[5]; a.rnd.normal[ray * 3 + 2] = vs[6]; }
-            if (a.rnd.depth) a.rnd.depth[ray] = vs[7] / (acc + 1e-10f);
-            if (a.rnd.bg_transmittance) a.rnd.bg_transmittance[ray] = dens ? expf(-(float)tot) : (float)tot;
-          }
-        }
-      }
-      named_sync(2, kEpiThreads);     // `red` / `racc` are rewritten by the next tile
-      TC_STAMP(15);
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  cluster_sync_all();                 // no CTA of the pair may release its TMEM / exit while the other one's MMAs could still touch it
-  if (warp == 0) tmem_dealloc2<512>(tmem);
-}
-
 // -----------------------------------------------------------------------------------------------------------------
 // host side
 // -----------------------------------------------------------------------------------------------------------------
-static size_t tc_layer_bytes(int planes, int Np, int nkb) { return (size_t)nkb * planes * Np * kKB * 2; }
+static size_t tc_layer_bytes(int planes, int Np, int nkb, int kblk) { return (size_t)nkb * planes * Np * kblk * 2; }
 
 struct TcPlan {
   int planes;
@@ -902,13 +62,14 @@ struct TcPlan {
 static void make_tc_plan(const sdfb200_field_t& f, const FieldPlan& p, TcPlan& t) {
   t.planes = f.precision == SDFB200_PRECISION_BF16X3 ? 2 : 1;
   const int np[L_COUNT] = {256, 256, 256, kInK, 256, 256, 256};
-  const int nkb[L_COUNT] = {kInK / kKB, 8, 8, 8, 8, kInK / kKB, 8};
+  const int kdim[L_COUNT] = {kInK, 256, 256, 256, 256, kInK, 256};
   size_t off = p.tc_off;
   for (int l = 0; l < L_COUNT; ++l) {
     t.layer[l].w_off = off;
     t.layer[l].Np = np[l];
-    t.layer[l].nkb = nkb[l];
-    off = align_up(off + tc_layer_bytes(t.planes, np[l], nkb[l]), 256);
+    t.layer[l].kblk = np[l] <= 128 ? kKBMax : kKB;
+    t.layer[l].nkb = kdim[l] / t.layer[l].kblk;
+    off = align_up(off + tc_layer_bytes(t.planes, np[l], t.layer[l].nkb, t.layer[l].kblk), 256);
   }
   t.wc_off = off;                       // fp32 [256][256]: Wgf * W2[1:,:]   (colour layer 0 applied to h2 directly)
   off = align_up(off + 256 * 256 * 4, 256);
@@ -952,8 +113,8 @@ int field_tc_pack(const sdfb200_field_t& f, const FieldPlan& p, char* blob, cuda
   for (int i = 0; i < kInK; ++i) ident.src[i] = (short)i;
   auto pack = [&](int L, const float* W, int ldw, int N, int K, const IdxMap* colmap, const IdxMap* rowmap) -> int {
     const TcLayer& ly = t.layer[L];
-    const int tot = ly.nkb * ly.Np * kKB;
-    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, t.planes, colmap != nullptr, colmap ? *colmap : ident, rowmap != nullptr,
+    const int tot = ly.nkb * ly.Np * ly.kblk;
+    k_tc_pack<<<(tot + 255) / 256, 256, 0, st>>>(W, ldw, N, K, ly.Np, ly.nkb, ly.kblk, t.planes, colmap != nullptr, colmap ? *colmap : ident, rowmap != nullptr,
                                                  rowmap ? *rowmap : ident, (__nv_bfloat16*)(blob + ly.w_off));
     SDFB_LAUNCHED("k_tc_pack");
     return 0;
@@ -1033,22 +194,13 @@ int field_tc_forward(const sdfb200_field_t& f, const FieldPlan& p, const char* b
   const int pairs = a.n_tile_pairs < tc_max_pairs() ? a.n_tile_pairs : tc_max_pairs();
   const int grid = 2 * pairs;
   const size_t smem = 2 * (size_t)t.planes * (kInK / 8) * 2048 + (size_t)kStages * t.planes * 128 * kKB * 2 + (6 * 128 + 9 * 256 + 32 + 12) * 4 + 1024;
-  if (t.planes == 2) {
-    SDFB_CUDA(cudaFuncSetAttribute(k_field_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_field_tc<2><<<grid, kTcThreads, smem, st>>>(a);
-  } else {
-    SDFB_CUDA(cudaFuncSetAttribute(k_field_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_field_tc<1><<<grid, kTcThreads, smem, st>>>(a);
-  }
-  SDFB_LAUNCHED("k_field_tc");
+  const bool torch_layout = f.grid.layout == SDFB200_GRID_TORCH;
+  if (t.planes == 2) return torch_layout ? launch_field_tc_p2_torch(a, grid, smem, st) : launch_field_tc_p2_tcnn(a, grid, smem, st);
+  return torch_layout ? launch_field_tc_p1_torch(a, grid, smem, st) : launch_field_tc_p1_tcnn(a, grid, smem, st);
   return 0;
 }
 
 }  // namespace sdfb200
 
-#ifdef SDFB200_TC_TIMING
-extern "C" int sdfb200_debug_tc_timing(long long* host_out_512) {
-  SDFB_CUDA(cudaMemcpyFromSymbol(host_out_512, sdfb200::g_tc_timing, sizeof(long long) * 512));
-  return 0;
-}
-#endif
+
+

@@ -206,13 +206,128 @@ __device__ __forceinline__ void encode_level_tcnn(const sdfb200_grid_t& g, const
   }
 }
 
-template <typename T, int F, bool GRAD, bool HINT = false>
+// LAYOUT < 0: decided at run time from g.layout; otherwise compile-time (the dead branch is dropped: code size matters for the
+// warp-specialised fused kernel, whose roles compete for the instruction cache)
+template <typename T, int F, bool GRAD, bool HINT = false, int LAYOUT = -1>
 __device__ __forceinline__ void encode_level(const sdfb200_grid_t& g, const void* table, int l, float x, float y, float z,
                                              float (&out)[F], float (&dout)[F][3], uint64_t pol = 0) {
-  if (g.layout == SDFB200_GRID_TORCH)
+  if (LAYOUT < 0 ? g.layout == SDFB200_GRID_TORCH : LAYOUT == SDFB200_GRID_TORCH)
     encode_level_torch<T, F, GRAD, HINT>(g, table, l, x, y, z, out, dout, pol);
   else
     encode_level_tcnn<T, F, GRAD, HINT>(g, table, l, x, y, z, out, dout, pol);
+}
+
+
+// -----------------------------------------------------------------------------------------------------------------
+// Split form of encode_level for software-pipelined gathers: prepare (indices + weights), fetch (8 loads), finish (blend).
+// prepare + fetch + finish computes exactly what encode_level computes (same expression trees), so several levels can have
+// their 8 gathers in flight together.
+// -----------------------------------------------------------------------------------------------------------------
+struct LevelCtx {
+  uint32_t idx[8];   // table rows relative to `base`; torch corner order (c,c,c)(c,f,c)(f,f,c)(f,c,c)(c,c,f)(c,f,f)(f,f,f)(f,c,f), tcnn: bit0=x bit1=y bit2=z
+  uint64_t base;
+  float w[3], dw[3], s;
+};
+
+template <int LAYOUT = -1>
+__device__ __forceinline__ void level_prepare(const sdfb200_grid_t& g, int l, float x, float y, float z, LevelCtx& c) {
+  const float s = g.scale[l];
+  c.s = s;
+  c.base = g.offset[l];
+  if (LAYOUT < 0 ? g.layout == SDFB200_GRID_TORCH : LAYOUT == SDFB200_GRID_TORCH) {
+    const float sx = __fmul_rn(x, s), sy = __fmul_rn(y, s), sz = __fmul_rn(z, s);
+    const float fxf = floorf(sx), fyf = floorf(sy), fzf = floorf(sz);
+    const uint32_t fx = (uint32_t)(int)fxf, fy = (uint32_t)(int)fyf, fz = (uint32_t)(int)fzf;
+    const uint32_t cx = (uint32_t)(int)ceilf(sx), cy = (uint32_t)(int)ceilf(sy), cz = (uint32_t)(int)ceilf(sz);
+    float ox = __fsub_rn(sx, fxf), oy = __fsub_rn(sy, fyf), oz = __fsub_rn(sz, fzf);
+    c.dw[0] = c.dw[1] = c.dw[2] = 1.f;
+    if (g.smoothstep) {
+      c.dw[0] = 6.f * ox * (1.f - ox); c.dw[1] = 6.f * oy * (1.f - oy); c.dw[2] = 6.f * oz * (1.f - oz);
+      ox = __fmul_rn(__fmul_rn(ox, ox), __fsub_rn(3.0f, __fmul_rn(2.0f, ox)));
+      oy = __fmul_rn(__fmul_rn(oy, oy), __fsub_rn(3.0f, __fmul_rn(2.0f, oy)));
+      oz = __fmul_rn(__fmul_rn(oz, oz), __fsub_rn(3.0f, __fmul_rn(2.0f, oz)));
+    }
+    c.w[0] = ox; c.w[1] = oy; c.w[2] = oz;
+    const uint32_t mask = (1u << g.log2_hashmap_size) - 1u;
+    const uint32_t hyc = cy * kPrimeY, hyf = fy * kPrimeY, hzc = cz * kPrimeZ, hzf = fz * kPrimeZ;
+    c.idx[0] = (cx ^ hyc ^ hzc) & mask; c.idx[1] = (cx ^ hyf ^ hzc) & mask; c.idx[2] = (fx ^ hyf ^ hzc) & mask; c.idx[3] = (fx ^ hyc ^ hzc) & mask;
+    c.idx[4] = (cx ^ hyc ^ hzf) & mask; c.idx[5] = (cx ^ hyf ^ hzf) & mask; c.idx[6] = (fx ^ hyf ^ hzf) & mask; c.idx[7] = (fx ^ hyc ^ hzf) & mask;
+  } else {
+    const uint32_t res = g.resolution[l], size = g.size[l];
+    const bool hashed = g.hashed[l];
+    const float p[3] = {fmaf(x, s, 0.5f), fmaf(y, s, 0.5f), fmaf(z, s, 0.5f)};
+    uint32_t cell[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float fl = floorf(p[d]);
+      cell[d] = (uint32_t)(int)fl;
+      const float t = p[d] - fl;
+      if (g.smoothstep) { c.w[d] = t * t * (3.f - 2.f * t); c.dw[d] = 6.f * t * (1.f - t); }
+      else { c.w[d] = t; c.dw[d] = 1.f; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t ix = cell[0] + (k & 1), iy = cell[1] + ((k >> 1) & 1), iz = cell[2] + ((k >> 2) & 1);
+      const uint32_t idx = hashed ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
+      c.idx[k] = idx % size;
+    }
+  }
+}
+
+template <typename T, int F>
+__device__ __forceinline__ void level_fetch(const void* table, const LevelCtx& c, float (&v)[8][F], uint64_t pol) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) table_load_hint<T, F>(table, c.base + c.idx[k], v[k], pol);
+}
+
+// F = 2 table entries whose element type is only known at run time (g.table_dtype)
+__device__ __forceinline__ void level_fetch_rt2(const sdfb200_grid_t& g, const void* table, const LevelCtx& c, float (&v)[8][2], uint64_t pol) {
+  if (g.table_dtype == SDFB200_DT_F16) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) table_load_hint<__half, 2>(table, c.base + c.idx[k], v[k], pol);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) table_load_hint<float, 2>(table, c.base + c.idx[k], v[k], pol);
+  }
+}
+
+template <int F, int LAYOUT = -1>
+__device__ __forceinline__ void level_finish(const sdfb200_grid_t& g, const LevelCtx& c, const float (&v)[8][F], float (&out)[F], float (&dout)[F][3]) {
+  if (LAYOUT < 0 ? g.layout == SDFB200_GRID_TORCH : LAYOUT == SDFB200_GRID_TORCH) {
+    const float ox = c.w[0], oy = c.w[1], oz = c.w[2];
+    const float nx = __fsub_rn(1.f, ox), ny = __fsub_rn(1.f, oy), nz = __fsub_rn(1.f, oz);
+#pragma unroll
+    for (int f = 0; f < F; ++f) {
+      const float f03 = __fadd_rn(__fmul_rn(v[0][f], ox), __fmul_rn(v[3][f], nx));
+      const float f12 = __fadd_rn(__fmul_rn(v[1][f], ox), __fmul_rn(v[2][f], nx));
+      const float f56 = __fadd_rn(__fmul_rn(v[5][f], ox), __fmul_rn(v[6][f], nx));
+      const float f47 = __fadd_rn(__fmul_rn(v[4][f], ox), __fmul_rn(v[7][f], nx));
+      const float f0312 = __fadd_rn(__fmul_rn(f03, oy), __fmul_rn(f12, ny));
+      const float f4756 = __fadd_rn(__fmul_rn(f47, oy), __fmul_rn(f56, ny));
+      out[f] = __fadd_rn(__fmul_rn(f0312, oz), __fmul_rn(f4756, nz));
+      const float gx = ((v[0][f] - v[3][f]) * oy + (v[1][f] - v[2][f]) * ny) * oz + ((v[4][f] - v[7][f]) * oy + (v[5][f] - v[6][f]) * ny) * nz;
+      const float gy = (f03 - f12) * oz + (f47 - f56) * nz;
+      const float gz = f0312 - f4756;
+      dout[f][0] = gx * c.dw[0] * c.s; dout[f][1] = gy * c.dw[1] * c.s; dout[f][2] = gz * c.dw[2] * c.s;
+    }
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) { out[f] = 0.f; dout[f][0] = dout[f][1] = dout[f][2] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float wx = (k & 1) ? c.w[0] : 1.f - c.w[0], wy = (k & 2) ? c.w[1] : 1.f - c.w[1], wz = (k & 4) ? c.w[2] : 1.f - c.w[2];
+      const float wt = wx * wy * wz;
+#pragma unroll
+      for (int f = 0; f < F; ++f) {
+        out[f] = fmaf(wt, v[k][f], out[f]);
+        dout[f][0] += ((k & 1) ? 1.f : -1.f) * wy * wz * v[k][f];
+        dout[f][1] += ((k & 2) ? 1.f : -1.f) * wx * wz * v[k][f];
+        dout[f][2] += ((k & 4) ? 1.f : -1.f) * wx * wy * v[k][f];
+      }
+    }
+#pragma unroll
+    for (int f = 0; f < F; ++f) { dout[f][0] *= c.dw[0] * c.s; dout[f][1] *= c.dw[1] * c.s; dout[f][2] *= c.dw[2] * c.s; }
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------

@@ -134,25 +134,15 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on an mbarrier of another CTA of the cluster.  Default (.release.cta) semantics, like cutlass::arch::ClusterBarrier::arrive:
+// what crosses the CTA boundary here is tensor memory (ordered by tcgen05.fence::before/after_thread_sync around the barrier) and
+// shared memory read by the async proxy (fence.proxy.async before the arrive) -- no global-memory hand-off needs cluster scope.
+// (.release.cluster / .acquire.cluster make ptxas emit a full memory barrier per arrive and an L1 invalidation, CCTL.IVALL, per
+// wait: measured as membar stalls and a 13 % L1 hit rate for the coarse hash levels.)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// wait with cluster-scope acquire (the arrivals come from the other CTA of the pair)
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {
-  }
-}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) { mbar_wait(bar, parity); }
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(COLS) : "memory");
