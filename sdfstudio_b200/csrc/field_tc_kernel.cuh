@@ -696,11 +696,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
           tmem_ld16(d_tmem + lane_addr + col0, v);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float c1 = fmaxf(__uint_as_float(v[j]) + p_bc1[col0 + j], 0.f);
-            r0 = fmaf(p_wc2[col0 + j], c1, r0);
-            r1 = fmaf(p_wc2[256 + col0 + j], c1, r1);
-            r2 = fmaf(p_wc2[512 + col0 + j], c1, r2);
+          for (int j = 0; j < 16; j += 4) {
+            // broadcast LDS.128: one shared-memory instruction per four columns and operand row instead of one per element
+            const float4 b4 = *reinterpret_cast<const float4*>(p_bc1 + col0 + j);
+            const float4 w0 = *reinterpret_cast<const float4*>(p_wc2 + col0 + j);
+            const float4 w1 = *reinterpret_cast<const float4*>(p_wc2 + 256 + col0 + j);
+            const float4 w2 = *reinterpret_cast<const float4*>(p_wc2 + 512 + col0 + j);
+            const float c0 = fmaxf(__uint_as_float(v[j]) + b4.x, 0.f), c1 = fmaxf(__uint_as_float(v[j + 1]) + b4.y, 0.f);
+            const float c2 = fmaxf(__uint_as_float(v[j + 2]) + b4.z, 0.f), c3 = fmaxf(__uint_as_float(v[j + 3]) + b4.w, 0.f);
+            r0 = fmaf(w0.x, c0, r0); r0 = fmaf(w0.y, c1, r0); r0 = fmaf(w0.z, c2, r0); r0 = fmaf(w0.w, c3, r0);
+            r1 = fmaf(w1.x, c0, r1); r1 = fmaf(w1.y, c1, r1); r1 = fmaf(w1.z, c2, r1); r1 = fmaf(w1.w, c3, r1);
+            r2 = fmaf(w2.x, c0, r2); r2 = fmaf(w2.y, c1, r2); r2 = fmaf(w2.z, c2, r2); r2 = fmaf(w2.w, c3, r2);
           }
         }
         named_sync(2, kEpiThreads);   // everyone has consumed the gradient partials in `red`
