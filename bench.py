@@ -42,17 +42,18 @@ FLOP_PER_SAMPLE_BAKED = 1071616  # 535 808 MAC
 WORKLOAD = "neus-facto-dtu65-4096x128"
 WORKLOADS = (WORKLOAD, "volsdf-errorbounded-4096", "bakedsdf-render-65536", "angelo-train-8192")
 AABB = [[-1.0, -1, -1], [1, 1, 1]]
+VOLSDF_BETA = 0.01   # Laplace beta of the volsdf workload: small like a trained scene, so that the error-bounded refinement loop actually iterates
 
 
 # ------------------------------------------------------------------------------------------------------------------ fields
-def make_field(device, precision="fp32", seed=0, table_dtype="fp32"):
+def make_field(device, precision="fp32", seed=0, table_dtype="fp32", beta_init=0.3):
     """The product SDFField of the headline workload (neus-facto preset, method_configs.py:472-480 + README override
     inside_outside=False), random-init + perturbation so that hash + PE inputs matter."""
     import sdfstudio_b200 as sb
     from sdfstudio_b200.synthetic import perturb_field_
 
     torch.manual_seed(seed)
-    cfg = sb.SDFFieldConfig(use_grid_feature=True, num_layers=2, num_layers_color=2, hidden_dim=256, bias=0.5, beta_init=0.3,
+    cfg = sb.SDFFieldConfig(use_grid_feature=True, num_layers=2, num_layers_color=2, hidden_dim=256, bias=0.5, beta_init=beta_init,
                             use_appearance_embedding=False, inside_outside=False, grid_layout="torch", precision=precision, table_dtype=table_dtype)
     field = sb.SDFField(cfg, torch.tensor(AABB), num_images=49)
     perturb_field_(field, seed)
@@ -206,7 +207,7 @@ def cpu_arm(workload, rays_per_step, steps, warmup):
         nears, fars = torch.full_like(nears, 0.2), torch.full_like(fars, 6.0)
         fn = lambda: oracle_step(oracle, o, d, cam, nears, fars, 48)  # noqa: E731  (field + compositing at the 48 final samples)
     elif workload == "volsdf-errorbounded-4096":
-        oracle = oracle_of(make_field("cpu"))
+        oracle = oracle_of(make_field("cpu", beta_init=VOLSDF_BETA))
         fn = lambda: oracle_step_volsdf(oracle, o, d, cam, nears, fars)  # noqa: E731
     else:
         oracle = oracle_of(make_field("cpu"))
@@ -273,7 +274,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
     if args.workload == "angelo-train-8192":
-        from tools import train_workload
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_workload
 
         return train_workload.main(args)
 
@@ -333,7 +335,7 @@ def main():
         cpu_sample = 256
     elif wl == "volsdf-errorbounded-4096":
         R = R_PER_GPU
-        field = make_field(dev, precision, table_dtype=args.table_dtype)
+        field = make_field(dev, precision, table_dtype=args.table_dtype, beta_init=VOLSDF_BETA)   # LaplaceDensity(beta_init=0.1); 0.01 = a trained-scene beta
         sampler = sb.ErrorBoundedSampler(num_samples=64, num_samples_eval=128, num_samples_extra=32, eps=0.1, beta_iters=10, max_total_iters=5).eval()
         o, d, cam, nears, fars = dtu_like_rays(R, 1000 + rank)
         counters = {"sdf_points": 0, "calls": 0}

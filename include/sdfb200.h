@@ -335,6 +335,27 @@ int sdfb200_weights_backward(const float* alphas_or_density, const float* euclid
                              float* g_in, void* stream);
 
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Training path: dense-layer GEMMs on tcgen05 (bf16x3 = parity grade, bf16 = fast), fp32 row-major in / out.  They replace the ATen /
+ * cuBLAS matmuls autograd runs for every nn.Linear of SDFField when the reference trains (sdf_field.py:400-409 through
+ * engine/trainer.py:319-323): forward Y = X W^T (+ bias, activation), input gradient dX = dY W, weight gradient dW = dY^T X.  The set is
+ * closed under differentiation (each one's backward is the other two), which is what the eikonal term's double backward needs
+ * (sdf_field.py:646-655, create_graph=True).  P = number of points (the long dimension); N, K = layer widths.  Buffers of width N / K
+ * must be allocated with their row padded to a multiple of 16 floats (ld >= pad16(width)); padding columns of outputs are written
+ * (zeros for epilogue 0), padding columns of inputs are ignored.  workspace >= sdfb200_gemm_workspace_bytes().
+ * epilogue: 0 none, 1 softplus(beta = 100), 2 relu.  bias [pad16(N)] or NULL.
+ * ------------------------------------------------------------------------------------------------------------- */
+size_t sdfb200_gemm_workspace_bytes(void);
+/* Y[P, N] = epilogue(X[P, K] W[N, K]^T + bias) */
+int sdfb200_gemm_nt(int32_t precision, const float* X, int64_t ldx, const float* W, int64_t ldw, int32_t N, int32_t K, const float* bias,
+                    int32_t epilogue, float* Y, int64_t ldy, int64_t P, void* workspace, size_t workspace_bytes, void* stream);
+/* Y[P, K] = X[P, N] W[N, K] */
+int sdfb200_gemm_nn(int32_t precision, const float* X, int64_t ldx, const float* W, int64_t ldw, int32_t N, int32_t K, float* Y, int64_t ldy,
+                    int64_t P, void* workspace, size_t workspace_bytes, void* stream);
+/* C[N, K] = A[P, N]^T B[P, K]  (reduction over the points; per-SM partial sums reduced in a fixed order: deterministic) */
+int sdfb200_gemm_tn(int32_t precision, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t P, int32_t N,
+                    int32_t K, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------*/
 int sdfb200_version(void);
 const char* sdfb200_last_error_string(void);

@@ -110,6 +110,10 @@ _PROTOS = {
     "sdfb200_render": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i64, _i32, C.POINTER(RenderOut), _vp]),
     "sdfb200_render_alphas": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp, C.POINTER(RenderOut), _vp]),
     "sdfb200_depth_clip": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "sdfb200_gemm_workspace_bytes": (_sz, []),
+    "sdfb200_gemm_nt": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "sdfb200_gemm_nn": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _i32, _i32, _vp, _i64, _i64, _vp, _sz, _vp]),
+    "sdfb200_gemm_tn": (C.c_int, [_i32, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i32, _i32, _vp, _sz, _vp]),
     "sdfb200_field_render_workspace_bytes": (_sz, [C.POINTER(FieldDesc), _i64, _i32]),
     "sdfb200_field_render": (C.c_int, [C.POINTER(FieldDesc), _vp, _vp, C.POINTER(FieldIn), C.POINTER(FieldOut), C.POINTER(FieldRender), _vp, _sz, _vp]),
 }

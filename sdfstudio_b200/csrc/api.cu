@@ -1,6 +1,7 @@
 // extern "C" entry points of the field (pack / forward) + library bookkeeping.  See include/sdfb200.h.
 #include "common.cuh"
 #include "field_plan.h"
+#include "tc_linear.h"
 
 #include <string.h>
 
@@ -204,3 +205,37 @@ extern "C" int sdfb200_field_render(const sdfb200_field_t* f, const void* packed
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Training path: the three GEMMs autograd needs for a Linear layer (forward / input gradient / weight gradient), closed under
+// differentiation (the backward of each is made of the other two), on the tcgen05 kernels of tc_linear.cu / tc_wgrad.cu.
+// ---------------------------------------------------------------------------------------------------------------------
+static int gemm_planes(int32_t precision) { return precision == SDFB200_PRECISION_BF16 ? 1 : 2; }
+
+extern "C" size_t sdfb200_gemm_workspace_bytes(void) { return tc_wgrad_workspace_bytes() + kTcGemmScratchBytes + 256; }
+
+extern "C" int sdfb200_gemm_nt(int32_t precision, const float* X, int64_t ldx, const float* W, int64_t ldw, int32_t N, int32_t K, const float* bias,
+                               int32_t epilogue, float* Y, int64_t ldy, int64_t P, void* workspace, size_t workspace_bytes, void* stream) {
+  SDFB_REQUIRE(precision == SDFB200_PRECISION_BF16X3 || precision == SDFB200_PRECISION_BF16, "gemm: precision must be bf16x3 or bf16");
+  SDFB_REQUIRE(X && W && Y && workspace && workspace_bytes >= kTcGemmScratchBytes, "gemm_nt: NULL pointer / workspace too small");
+  SDFB_REQUIRE(epilogue == TCL_NONE || epilogue == TCL_SOFTPLUS || epilogue == TCL_RELU, "gemm_nt: epilogue");
+  SDFB_REQUIRE(N >= 1 && K >= 1 && ldx >= pad16(K) && ldy >= pad16(N) && ldx % 4 == 0 && ldy % 4 == 0, "gemm_nt: X / Y must hold the dims padded to 16");
+  return tc_gemm_ex(gemm_planes(precision), epilogue, X, (int)ldx, W, (int)ldw, 0, N, K, bias, Y, (int)ldy, P, pad16(N), pad16(K), nullptr, 0, 0, workspace,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_gemm_nn(int32_t precision, const float* X, int64_t ldx, const float* W, int64_t ldw, int32_t N, int32_t K, float* Y, int64_t ldy,
+                               int64_t P, void* workspace, size_t workspace_bytes, void* stream) {
+  SDFB_REQUIRE(precision == SDFB200_PRECISION_BF16X3 || precision == SDFB200_PRECISION_BF16, "gemm: precision must be bf16x3 or bf16");
+  SDFB_REQUIRE(X && W && Y && workspace && workspace_bytes >= kTcGemmScratchBytes, "gemm_nn: NULL pointer / workspace too small");
+  SDFB_REQUIRE(N >= 1 && K >= 1 && ldx >= pad16(N) && ldy >= pad16(K) && ldx % 4 == 0 && ldy % 4 == 0, "gemm_nn: X / Y must hold the dims padded to 16");
+  // Y[P, K] = X[P, N] W[N, K]  ==  X (W^T)^T : the weight tile is packed from the transposed view
+  return tc_gemm_ex(gemm_planes(precision), TCL_NONE, X, (int)ldx, W, (int)ldw, 1, K, N, nullptr, Y, (int)ldy, P, pad16(K), pad16(N), nullptr, 0, 0, workspace,
+                    (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_gemm_tn(int32_t precision, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t P, int32_t N,
+                               int32_t K, void* workspace, size_t workspace_bytes, void* stream) {
+  SDFB_REQUIRE(precision == SDFB200_PRECISION_BF16X3 || precision == SDFB200_PRECISION_BF16, "gemm: precision must be bf16x3 or bf16");
+  return tc_wgrad(gemm_planes(precision), A, lda, B, ldb, C, ldc, P, N, K, workspace, workspace_bytes, (cudaStream_t)stream);
+}

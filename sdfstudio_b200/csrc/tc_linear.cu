@@ -33,14 +33,15 @@ __device__ __forceinline__ float tcl_softplus100(float z) {
 __device__ __forceinline__ float tcl_dsoftplus_from_h(float h) { return 1.0f - tcl_ex2(h * -144.26950408889634f); }
 
 // fp32 W[n, k] (row stride ldw) -> bf16 split planes [K-block][plane][k/8][n][8], zero padded to (Ncp, nblocks*32)
-__global__ void k_tcl_pack(const float* __restrict__ W, int ldw, int N, int K, int Ncp, int nblocks, int planes, __nv_bfloat16* __restrict__ out) {
+// trans != 0: the source holds the matrix transposed (element (n, k) at W[k * ldw + n]) -- the dgrad GEMM dX = dY W packs W^T this way
+__global__ void k_tcl_pack(const float* __restrict__ W, int ldw, int N, int K, int Ncp, int nblocks, int planes, int trans, __nv_bfloat16* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= nblocks * Ncp * kKBL) return;
   const int kk = idx % kKBL;
   const int n = (idx / kKBL) % Ncp;
   const int b = idx / (kKBL * Ncp);
   const int k = b * kKBL + kk;
-  const float w = (n < N && k < K) ? W[(size_t)n * ldw + k] : 0.f;
+  const float w = (n < N && k < K) ? (trans ? W[(size_t)k * ldw + n] : W[(size_t)n * ldw + k]) : 0.f;
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const size_t plane_elems = (size_t)Ncp * kKBL;
   const size_t off = (size_t)b * planes * plane_elems + (size_t)(kk / 8) * (Ncp * 8) + (size_t)n * 8 + (kk % 8);
@@ -183,7 +184,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
       if (lane * 4 < ncols) {
         const int n = nbase + lane * 4;                     // column inside this N chunk
         float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (a.final_chunk && EPI != TCL_MUL_DSOFTPLUS) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
+        if (a.final_chunk && EPI != TCL_MUL_DSOFTPLUS && a.bias != nullptr) bv = __ldg(reinterpret_cast<const float4*>(a.bias + n));
         const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
         // operands that come from global memory (previous partial sums, softplus' source) are fetched for all 8 rows of this warp first
         const bool want_aux = a.final_chunk && EPI == TCL_MUL_DSOFTPLUS && a.n0 + n < a.aux_cols;
@@ -255,6 +256,13 @@ int launch_linear(int epi, const LinArgs& a, size_t smem, unsigned grid, cudaStr
 
 int tc_gemm(int planes, int epi, const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M, int Np, int Kp,
             const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st) {
+  return tc_gemm_ex(planes, epi, X, ldx, W, Kp, 0, Np, Kp, bias, Y, ldy, M, Np, Kp, aux, ldaux, aux_cols, scratch, st);
+}
+
+// general form: W is [Nw, Kw] with row stride ldw (or its transpose when trans_w), zero padded on the fly to (Np, Kp); bias may be NULL for
+// TCL_NONE (no bias added)
+int tc_gemm_ex(int planes, int epi, const float* X, int ldx, const float* W, int ldw, int trans_w, int Nw, int Kw, const float* bias, float* Y, int ldy,
+               int64_t M, int Np, int Kp, const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st) {
   SDFB_REQUIRE(planes == 1 || planes == 2, "tc_gemm: planes");
   SDFB_REQUIRE(Np % 16 == 0 && Kp % 16 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "tc_gemm: dims must be padded to 16");
   SDFB_REQUIRE(scratch != nullptr, "tc_gemm: scratch is NULL");
@@ -266,13 +274,15 @@ int tc_gemm(int planes, int epi, const float* X, int ldx, const float* W, const 
       const int Kc = Kp - k0 < 256 ? Kp - k0 : 256;
       const int Kc32 = (Kc + 31) / 32 * 32, nblocks = Kc32 / kKBL;
       const int tot = nblocks * Nc * kKBL;
-      k_tcl_pack<<<(tot + 255) / 256, 256, 0, st>>>(W + (size_t)n0 * Kp + k0, Kp, Nc, Kc, Nc, nblocks, planes, (__nv_bfloat16*)scratch);
+      const float* wsrc = trans_w ? W + (size_t)k0 * ldw + n0 : W + (size_t)n0 * ldw + k0;
+      const int nv = Nw - n0 < Nc ? (Nw - n0 > 0 ? Nw - n0 : 0) : Nc, kv = Kw - k0 < Kc ? (Kw - k0 > 0 ? Kw - k0 : 0) : Kc;
+      k_tcl_pack<<<(tot + 255) / 256, 256, 0, st>>>(wsrc, ldw, nv, kv, Nc, nblocks, planes, trans_w, (__nv_bfloat16*)scratch);
       SDFB_LAUNCHED("k_tcl_pack");
       LinArgs a;
-      a.X = X + k0; a.ldx = ldx; a.M = M; a.Kc32 = Kc32; a.Kvalid = Kc; a.Wp = (const __nv_bfloat16*)scratch; a.Ncp = Nc;
+      a.X = X + k0; a.ldx = ldx; a.M = M; a.Kc32 = Kc32; a.Kvalid = kv; a.Wp = (const __nv_bfloat16*)scratch; a.Ncp = Nc;
       a.bias = bias ? bias + n0 : nullptr; a.Y = Y; a.ldy = ldy; a.n0 = n0; a.accumulate = k0 > 0; a.final_chunk = k0 + 256 >= Kp;
       a.aux = aux; a.ldaux = ldaux; a.aux_cols = aux_cols;
-      if (epi != TCL_MUL_DSOFTPLUS) SDFB_REQUIRE(bias != nullptr, "tc_gemm: bias is NULL");
+      if (epi != TCL_MUL_DSOFTPLUS && epi != TCL_NONE) SDFB_REQUIRE(bias != nullptr, "tc_gemm: bias is NULL");
       const size_t smem = (size_t)kRingBytesL + kStageTileBytesL + 1024;
       const int r = planes == 2 ? launch_linear<2>(epi, a, smem, grid, st) : launch_linear<1>(epi, a, smem, grid, st);
       if (r) return r;

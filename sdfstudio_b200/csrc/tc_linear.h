@@ -13,4 +13,12 @@ constexpr size_t kTcGemmScratchBytes = 2ull * 256 * 256 * 2;                    
 int tc_gemm(int planes, int epi, const float* X, int ldx, const float* W, const float* bias, float* Y, int ldy, int64_t M, int Np, int Kp,
             const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st);
 
+int tc_gemm_ex(int planes, int epi, const float* X, int ldx, const float* W, int ldw, int trans_w, int Nw, int Kw, const float* bias, float* Y, int ldy,
+               int64_t M, int Np, int Kp, const float* aux, int ldaux, int aux_cols, void* scratch, cudaStream_t st);
+
+// weight-gradient GEMM (csrc/tc_wgrad.cu): C[N, K] = A[P, N]^T B[P, K]
+size_t tc_wgrad_workspace_bytes();
+int tc_wgrad(int planes, const float* A, long long lda, const float* B, long long ldb, float* C, long long ldc, int64_t P, int N, int K, void* workspace,
+             size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace sdfb200

@@ -121,6 +121,7 @@ class SDFFieldConfig:
     grid_layout: str = "tcnn"      # "tcnn" (checkpoint compatible) | "torch" (reference HashEncoding layout)
     precision: str = "fp32"        # "fp32" | "bf16x3" | "bf16"   (include/sdfb200.h SDFB200_PRECISION_*)
     table_dtype: str = "fp32"      # "fp32" | "fp16": gather from an fp16 copy of the table (tiny-cuda-nn's own storage precision)
+    train_gemm: str = "auto"       # training-mode dense layers: "auto" = tcgen05 GEMMs (linear_ops.py) unless precision == "fp32"; "aten" | "tc"
 
     def setup(self, **kwargs):
         return self._target(self, **kwargs)

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
+from . import linear_ops as _lo
 from .field_heads import FieldHeadNames
 
 # 21 icosahedron directions of the off-axis encoding (field_components/encodings.py:129-153), [3, 21]
@@ -36,6 +37,38 @@ def nerf_encoding(x, num_frequencies: int, max_exp: float, include_input: bool, 
     return torch.cat([enc, x], dim=-1) if include_input else enc
 
 
+def _gemm_precision(field):
+    """None -> ATen matmuls (precision "fp32": exact reference arithmetic); otherwise the tcgen05 GEMMs of linear_ops at that precision."""
+    mode = getattr(field.config, "train_gemm", "auto")
+    prec = getattr(field.config, "precision", "fp32")
+    if mode == "aten" or (mode == "auto" and prec == "fp32"):
+        return None
+    return "bf16" if prec == "bf16" else "bf16x3"
+
+
+def _weight_of(lin):
+    """the effective weight of a (weight-normed) nn.Linear, with autograd history to weight_g / weight_v (sdf_field.py:312-313)"""
+    if hasattr(lin, "weight_v"):
+        return torch._weight_norm(lin.weight_v, lin.weight_g, 0)
+    return lin.weight
+
+
+def _dense(field, lin, x, act: int = 0):
+    """act(lin(x)) with act 0 none / 1 softplus(beta=100) / 2 relu.  x may carry zero padding columns beyond lin.in_features; on the
+    tensor-core path the result is padded to a multiple of 16 columns (callers slice what they need)."""
+    prec = _gemm_precision(field)
+    k, n = lin.in_features, lin.out_features
+    if prec is None:
+        y = lin(x[:, :k] if x.shape[1] != k else x)
+        return F.softplus(y, beta=100) if act == 1 else (torch.relu(y) if act == 2 else y)
+    kp = _lo.pad16(k)
+    if x.shape[1] < kp:
+        x = F.pad(x, (0, kp - x.shape[1]))
+    elif x.shape[1] > kp:
+        x = x[:, :kp]
+    return _lo.linear(x, _weight_of(lin), lin.bias, act, prec)
+
+
 def forward_geonetwork(field, inputs):
     """sdf_field.py:380-410."""
     c = field.config
@@ -53,11 +86,9 @@ def forward_geonetwork(field, inputs):
     for l in range(0, field.num_layers - 1):
         lin = getattr(field, "glin" + str(l))
         if l in field.skip_in:
-            x = torch.cat([x, inputs], 1) / np.sqrt(2)
-        x = lin(x)
-        if l < field.num_layers - 2:
-            x = F.softplus(x, beta=100)
-    return x
+            x = torch.cat([x[:, : lin.in_features - inputs.shape[1]], inputs], 1) / np.sqrt(2)
+        x = _dense(field, lin, x, 1 if l < field.num_layers - 2 else 0)
+    return x[:, : lin.out_features] if x.shape[1] != lin.out_features else x
 
 
 def gradient(field, x, skip_spatial_distortion=False, return_sdf=False):
@@ -110,10 +141,8 @@ def get_colors(field, points, directions, gradients, geo_features, camera_indice
         h.append(torch.sum(normals * directions, dim=-1, keepdim=True))
     h = torch.cat(h, dim=-1)
     for l in range(0, field.num_layers_color - 1):
-        h = getattr(field, "clin" + str(l))(h)
-        if l < field.num_layers_color - 2:
-            h = torch.relu(h)
-    rgb = torch.sigmoid(h)
+        h = _dense(field, getattr(field, "clin" + str(l)), h, 2 if l < field.num_layers_color - 2 else 0)
+    rgb = torch.sigmoid(h[:, :3])
     if c.use_diffuse_color:
         diffuse_linear = torch.sigmoid(raw_rgb_diffuse - math.log(3.0))
         specular_linear = tint * rgb if c.use_specular_tint else 0.5 * rgb

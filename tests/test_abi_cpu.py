@@ -171,7 +171,7 @@ def test_mirror_signatures_and_config_defaults_match_reference():
         return f"<{type(v).__name__}>"
 
     mine_cfg = {f.name: plain(f.default) for f in dataclasses.fields(sb.SDFFieldConfig) if f.name != "_target" and f.default is not dataclasses.MISSING}
-    b200_knobs = {"grid_layout", "precision", "table_dtype"}
+    b200_knobs = {"grid_layout", "precision", "table_dtype", "train_gemm"}
     assert {k: v for k, v in mine_cfg.items() if k not in b200_knobs} == ref["SDFFieldConfig"]
     problems = []
     for name, sig in ref.items():

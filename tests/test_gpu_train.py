@@ -186,11 +186,15 @@ def _oracle_loss(of: OracleField, spec, o, d, cam, starts, deltas, bins, target,
     return loss, out_rgb
 
 
+@pytest.mark.parametrize("gemm", ["aten", "tc"])
 @pytest.mark.parametrize("case", ["neusfacto_c1", "bakedsdf_small"])
-def test_sdffield_training_step(case):
+def test_sdffield_training_step(case, gemm):
+    """gemm="aten": dense layers through ATen (fp32, the reference's own arithmetic); gemm="tc": forward, input-gradient and
+    weight-gradient GEMMs -- incl. the eikonal double backward -- on the tcgen05 kernels (linear_ops.py, bf16x3)."""
     import sdfstudio_b200 as sb
 
     spec, kw, o, d, cam, nears, fars, oracle, field = build_case(case)
+    field.config.train_gemm, field.config.precision = gemm, ("bf16x3" if gemm == "tc" else "fp32")
     R, S = 48, 12
     o, d, cam, nears, fars = o[:R], d[:R], cam[:R], nears[:R], fars[:R]
     if spec.contraction is not None:
@@ -228,7 +232,7 @@ def test_sdffield_training_step(case):
                                  lambda p: scene_contraction(p, spec.contraction))
     loss_r.backward()
 
-    assert abs(float(loss_c.detach()) - float(loss_r.detach())) < 5e-5 * max(1.0, abs(float(loss_r.detach())))
+    assert abs(float(loss_c.detach()) - float(loss_r.detach())) < (5e-5 if gemm == "aten" else 2e-4) * max(1.0, abs(float(loss_r.detach())))
     assert _maxrel(res["rgb"], rgb_r) < 5e-4          # fp32 cancellation in the NeuS alpha (prev_cdf - next_cdf), same as the reference in fp32
     name_map = {"hash_table": "encoding.hash_table" if spec.grid_layout == "torch" else "encoding.params"}
     sd = dict(field.named_parameters())
@@ -254,7 +258,74 @@ def test_sdffield_training_step(case):
     with torch.no_grad():
         fo2 = field(rs, return_alphas=True)
     for key in (sb.FieldHeadNames.RGB, sb.FieldHeadNames.SDF, sb.FieldHeadNames.GRADIENT, sb.FieldHeadNames.ALPHA):
-        assert _maxrel(fo2[key], fo[key]) < 1e-4, key
+        assert _maxrel(fo2[key], fo[key]) < (1e-4 if gemm == "aten" else 5e-4), key
+
+
+# ------------------------------------------------------------------------------------------------------------------ training GEMMs
+@pytest.mark.parametrize("P,N,K", [(1000, 256, 71), (4097, 257, 256), (333, 3, 256), (2500, 256, 321), (77, 16, 16)])
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_training_gemm_primitives(P, N, K, precision):
+    """sdfb200_gemm_nt / _nn / _tn (tcgen05) against fp64 matmuls: Y = X W^T, dX = dY W, dW = dY^T X."""
+    from sdfstudio_b200 import linear_ops as lo
+
+    g = torch.Generator().manual_seed(P + N + K)
+    x = torch.randn(P, K, generator=g) * 0.5
+    W = torch.randn(N, K, generator=g) / K**0.5
+    gy = torch.randn(P, N, generator=g)
+    xp, gyp = lo.pad_cols(x).cuda(), lo.pad_cols(gy).cuda()
+    tol = 3e-5 if precision == "bf16x3" else 8e-3
+
+    def relerr(a, ref, scale):
+        return float((a.double().cpu() - ref).abs().max()) / scale
+
+    y = lo.gemm_nt(xp, W.cuda(), precision)
+    assert y.shape == (P, lo.pad16(N)) and float(y[:, N:].abs().max() if N % 16 else 0.0) == 0.0
+    assert relerr(y[:, :N], x.double() @ W.double().t(), float((x.abs().double() @ W.abs().double().t()).max())) < tol
+    dx = lo.gemm_nn(gyp, W.cuda(), precision)
+    assert dx.shape == (P, lo.pad16(K))
+    assert relerr(dx[:, :K], gy.double() @ W.double(), float((gy.abs().double() @ W.abs().double()).max())) < tol
+    dW = lo.gemm_tn(gyp, xp, N, K, precision)
+    assert dW.shape == (N, K)
+    assert relerr(dW, gy.double().t() @ x.double(), float((gy.abs().double().t() @ x.abs().double()).max())) < tol
+    # determinism of the weight gradient (fixed-order reduction of the per-SM partial sums)
+    assert torch.equal(dW, lo.gemm_tn(gyp, xp, N, K, precision))
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_training_linear_first_and_second_order(act):
+    """linear_ops.linear (fused bias + activation epilogue) under autograd, incl. create_graph=True double backward (the eikonal pattern:
+    a loss on d out / d x), against the same composition in fp64 ATen."""
+    import torch.nn.functional as F
+
+    from sdfstudio_b200 import linear_ops as lo
+
+    g = torch.Generator().manual_seed(5 + act)
+    P, K, H = 777, 39, 256
+    x0 = torch.randn(P, K, generator=g) * 0.3
+    W0, b0 = torch.randn(H, K, generator=g) / K**0.5 * 0.3, torch.randn(H, generator=g) * 0.02
+    W1, b1 = torch.randn(1, H, generator=g) / H**0.5, torch.randn(1, generator=g) * 0.1
+    coef = torch.randn(P, generator=g)
+
+    def run(lin, x, params, dt):
+        W0_, b0_, W1_, b1_ = params
+        h = lin(x, W0_, b0_, act)
+        y = lin(h, W1_, b1_, 0)[:, :1]
+        (gx,) = torch.autograd.grad(y.sum(), x, create_graph=True)
+        loss = (y[:, 0] * coef.to(y.device, dt)).sum() + ((gx[:, :K].norm(dim=-1) - 1) ** 2).mean()
+        return loss, torch.autograd.grad(loss, params)
+
+    def ref_lin(x, W, b, a):
+        z = F.linear(x, W, b)
+        return F.softplus(z, beta=100) if a == 1 else (torch.relu(z) if a == 2 else z)
+
+    p64 = [t.double().requires_grad_(True) for t in (W0, b0, W1, b1)]
+    loss_r, grads_r = run(ref_lin, x0.double().requires_grad_(True), p64, torch.float64)
+    pc = [t.cuda().requires_grad_(True) for t in (W0, b0, W1, b1)]
+    xc = lo.pad_cols(x0).cuda().requires_grad_(True)
+    loss_c, grads_c = run(lambda x, W, b, a: lo.linear(x, W, b, a, "bf16x3"), xc, pc, torch.float32)
+    assert abs(float(loss_c) - float(loss_r)) < 1e-4 * max(1.0, abs(float(loss_r)))
+    for gc, gr, name in zip(grads_c, grads_r, ("W0", "b0", "W1", "b1")):
+        assert _maxrel(gc, gr) < 2e-3, (name, _maxrel(gc, gr))
 
 
 # ------------------------------------------------------------------------------------------------------------------ proposal network

@@ -25,13 +25,14 @@ def main():
     ap.add_argument("--samples", type=int, default=64)
     ap.add_argument("--importance", type=int, default=64)
     ap.add_argument("--precision", default="bf16x3", help="precision of the no_grad (sampler) kernels")
+    ap.add_argument("--train-gemm", default="auto", choices=["auto", "tc", "aten"], help="dense layers of the training path: tcgen05 GEMMs (linear_ops) or ATen")
     ap.add_argument("--no-tf32", action="store_true", help="keep ATen matmuls in fp32 (the reference trains with TF32, scripts/train.py:59)")
     args = ap.parse_args()
     dev = torch.device("cuda")
     torch.backends.cuda.matmul.allow_tf32 = not args.no_tf32
     torch.manual_seed(0)
     cfg = sb.SDFFieldConfig(use_grid_feature=True, num_layers=2, num_layers_color=2, hidden_dim=256, bias=0.5, beta_init=0.3, inside_outside=False,
-                            grid_layout="torch", precision=args.precision)
+                            grid_layout="torch", precision=args.precision, train_gemm=args.train_gemm)
     field = synthetic.perturb_field_(sb.SDFField(cfg, torch.tensor([[-1.0, -1, -1], [1, 1, 1]]), num_images=49), 0).to(dev).train()
     sampler = sb.NeuSSampler(num_samples=args.samples, num_samples_importance=args.importance, num_samples_outside=0, num_upsample_steps=4).train()
     opt = torch.optim.Adam(field.parameters(), lr=5e-4, eps=1e-15)
@@ -82,7 +83,7 @@ def main():
         last = step(True)
     S = args.samples + args.importance
     print(json.dumps({"metric": "train rays/sec (NeuS sampler + SDFField fwd/bwd + Adam)", "value": R / ms * 1e3, "unit": "rays/s", "rays": R,
-                      "samples_per_ray": S, "ms_per_step": ms, "phase_ms": {k: v / 3 for k, v in acc.items()}, "loss": last, "tf32_matmul": not args.no_tf32,
+                      "samples_per_ray": S, "ms_per_step": ms, "phase_ms": {k: v / 3 for k, v in acc.items()}, "loss": last, "tf32_matmul": not args.no_tf32, "train_gemm": args.train_gemm,
                       "reference_note": "README-derived ~45k train-rays/s on RTX 3090 (SURVEY.md 8d iii)"}))
 
 
