@@ -38,6 +38,20 @@ __global__ void __launch_bounds__(256) k_grid_encode(const __grid_constant__ sdf
   }
 }
 
+// vector atomics (sm_90+: red.global.add.v2.f32 / .v4.f32): one L2 atomic per 8 / 16 bytes of a table row instead of one per float
+template <int F>
+__device__ __forceinline__ void atomic_add_row(float* dst, const float (&v)[F]) {
+  if constexpr (F % 4 == 0) {
+#pragma unroll
+    for (int f = 0; f < F; f += 4) atomicAdd(reinterpret_cast<float4*>(dst + f), make_float4(v[f], v[f + 1], v[f + 2], v[f + 3]));
+  } else if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(dst), make_float2(v[0], v[1]));
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) atomicAdd(dst + f, v[f]);
+  }
+}
+
 // backward: scatter dout into the table gradient, optional dx01.
 template <typename T, int F>
 __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__ sdfb200_grid_t g, const void* __restrict__ table,
@@ -70,8 +84,10 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__
       const float w = (bx ? o[0] : 1.f - o[0]) * (by ? o[1] : 1.f - o[1]) * (bz ? o[2] : 1.f - o[2]);
       const uint32_t h = (fc[0][bx] ^ (fc[1][by] * kPrimeY) ^ (fc[2][bz] * kPrimeZ)) & mask;
       float* dst = dtable + (base + h) * F;
+      float wv[F];
 #pragma unroll
-      for (int f = 0; f < F; ++f) atomicAdd(dst + f, w * go[f]);
+      for (int f = 0; f < F; ++f) wv[f] = w * go[f];
+      atomic_add_row<F>(dst, wv);
     }
   } else {
     const uint32_t res = g.resolution[l], size = g.size[l];
@@ -91,8 +107,10 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__
       uint32_t idx2 = hashed ? (ix ^ (iy * kPrimeY) ^ (iz * kPrimeZ)) : (ix + iy * res + iz * res * res);
       idx2 %= size;
       float* dst = dtable + (base + idx2) * F;
+      float wv[F];
 #pragma unroll
-      for (int f = 0; f < F; ++f) atomicAdd(dst + f, wt * go[f]);
+      for (int f = 0; f < F; ++f) wv[f] = wt * go[f];
+      atomic_add_row<F>(dst, wv);
     }
   }
   if (dx01 != nullptr) {
@@ -161,7 +179,12 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd2(const __grid_constant_
     for (int f = 0; f < F; ++f) {
       acc_do[f] = fmaf(gW, v[f], acc_do[f]);
       dot = fmaf(go[f], v[f], dot);
-      if (g_table) atomicAdd(g_table + row * F + f, gW * go[f]);
+    }
+    if (g_table) {
+      float wv[F];
+#pragma unroll
+      for (int f = 0; f < F; ++f) wv[f] = gW * go[f];
+      atomic_add_row<F>(g_table + row * F, wv);
     }
     if (g_x) {
       const float h00 = sg[0] * q.d2w[0] * A[1] * A[2], h11 = A[0] * sg[1] * q.d2w[1] * A[2], h22 = A[0] * A[1] * sg[2] * q.d2w[2];
