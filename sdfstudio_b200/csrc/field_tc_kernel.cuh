@@ -95,6 +95,14 @@ __device__ __forceinline__ void store_chunk(uint8_t* inA, int row, int chunk, co
 
 // accurate sin / sincos as real calls: one copy of the (long) range-reduction code instead of one per call site -- the roles of this
 // kernel share the SM's instruction cache, and `no instruction` stalls were 20 % of all samples with everything inlined
+// L2 eviction priorities (0 normal, 1 evict_first, 2 evict_last) of the hash table and of the per-CTA scratch spills (A/B measured)
+#ifndef TCV_POL_TABLE
+#define TCV_POL_TABLE 2
+#endif
+#ifndef TCV_POL_SCRATCH
+#define TCV_POL_SCRATCH 1
+#endif
+
 static __device__ __noinline__ void sincos_call(float x, float* s, float* c) { sincosf(x, s, c); }
 static __device__ __noinline__ float sin_call(float x) { return sinf(x); }
 
@@ -368,7 +376,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     const bool alu = warp >= kEpiWarps + kGatherWarps;
     const int row = alu ? (warp - kEpiWarps - kGatherWarps) * 32 + lane : (warp - kEpiWarps) * 32 + lane;
     uint8_t* enc_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta) + 65536 + (size_t)P * 65536;
-    const uint64_t pol_table = l2_policy_evict_last();
+    const uint64_t pol_table = l2_policy(TCV_POL_TABLE);
     auto encode = [&](int tile, uint8_t* inA, uint8_t* enc) {
       if (alu) { encode_tile_pe<P>(a, tile, row, inA, enc); encode_tile_pe<P>(a, tile, row + 64, inA, enc); }
       else encode_tile_grid<P, LAYOUT>(a, tile, row, inA, enc, pol_table);
@@ -416,7 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     uint8_t* gf_s = sig_s + 65536;                                                                      // [P][32 units][128][16 B]
     uint8_t* enc_s = gf_s + (size_t)P * 65536;                                                          // 2 x input jacobian
     uint32_t dpar = 0;
-    const uint64_t pol_stream = l2_policy_evict_first();
+    const uint64_t pol_stream = l2_policy(TCV_POL_SCRATCH);
     const uint64_t pol_keep = l2_policy_evict_normal();
     auto epi_arrive = [&]() {
       tc_fence_before();

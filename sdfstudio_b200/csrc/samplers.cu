@@ -223,61 +223,99 @@ __device__ __forceinline__ float volsdf_dstar(const float* e, const float* sd, i
   return (sg1 * sg0 == 1.f) ? ds : 0.f;
 }
 
-// get_error_bound (:740-756) for one ray at one beta: max_i (clamp(exp(E_i),1e6)-1) * exp(-I_i)
-__device__ float volsdf_error_bound(const float* e, const float* sd, int S, float beta) {
-  double integ = 0.0, errint = 0.0;
+// ONE WARP PER RAY.  get_error_bound (:740-756) at one beta:  max_i (clamp(exp(E_i), 1e6) - 1) * exp(-I_i) with the inclusive prefix
+// sum E_i of the section errors and the exclusive prefix sum I_i of delta * sigma -- both as warp scans in double carried across
+// 32-sample rows (not the sequential order of torch.cumsum: agreement at the 1e-7 level, like the compositing kernels).  Per-sample
+// quantities that do not depend on beta (delta, d*, sdf) are cached in shared memory once per ray.
+// torch.clamp and .max(-1) propagate NaN (a slightly negative Heron area gives sqrt(<0) = NaN d_star in the reference): fminf / fmaxf
+// would drop it, so it is carried explicitly -- a NaN bound leaves beta untouched, as in the reference.
+constexpr int kVolsdfMaxS = 1000;   // 4 rays x 3 x S floats of dynamic shared memory stay under the 48 KB default
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double o = __shfl_up_sync(0xffffffffu, v, d);
+    if (lane >= d) v += o;
+  }
+  return v;
+}
+__device__ float volsdf_error_bound_warp(const float* delta_s, const float* dstar_s, const float* sdf_s, int S, float beta, int lane) {
+  double carryE = 0.0, carryI = 0.0;
   float best = -INFINITY;
   bool saw_nan = false;
   const float b2 = __fmul_rn(4.0f, __fmul_rn(beta, beta));
-  for (int i = 0; i < S; ++i) {
-    const float delta = __fsub_rn(e[i + 1], e[i]);
-    const float ds = volsdf_dstar(e, sd, i < S - 1 ? i : S - 2);
-    const float err_sec = __fdiv_rn(__fmul_rn(expf(__fdiv_rn(-ds, beta)), __fmul_rn(delta, delta)), b2);
-    errint += (double)err_sec;
-    // torch.clamp and .max(-1) propagate NaN (a slightly negative Heron area gives sqrt(<0) = NaN d_star in the reference):
-    // fminf / fmaxf would drop it, so it is carried explicitly -- a NaN bound leaves beta untouched, as in the reference
-    const float ef = expf((float)errint);
-    const float bound = __fmul_rn(__fsub_rn(ef != ef ? ef : fminf(ef, 1.0e6f), 1.0f), expf(-(float)integ));
-    if (bound != bound) saw_nan = true;
-    else best = fmaxf(best, bound);
-    integ += (double)__fmul_rn(delta, laplace_density(sd[i], beta));
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int i = s0 + lane;
+    const bool on = i < S;
+    const float delta = on ? delta_s[i] : 0.f;
+    const float err_sec = on ? __fdiv_rn(__fmul_rn(expf(__fdiv_rn(-dstar_s[i], beta)), __fmul_rn(delta, delta)), b2) : 0.f;
+    const float dd = on ? __fmul_rn(delta, laplace_density(sdf_s[i], beta)) : 0.f;
+    const double einc = warp_scan_incl((double)err_sec, lane);
+    const double iinc = warp_scan_incl((double)dd, lane);
+    const float E = (float)(carryE + einc), I = (float)(carryI + iinc - (double)dd);
+    const float ef = expf(E);
+    const float bound = __fmul_rn(__fsub_rn(ef != ef ? ef : fminf(ef, 1.0e6f), 1.0f), expf(-I));
+    if (on) {
+      if (bound != bound) saw_nan = true;
+      else best = fmaxf(best, bound);
+    }
+    carryE += __shfl_sync(0xffffffffu, einc, 31);
+    carryI += __shfl_sync(0xffffffffu, iinc, 31);
   }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, d));
+  saw_nan = __any_sync(0xffffffffu, saw_nan);
   return saw_nan ? __int_as_float(0x7fc00000) : best;
 }
 
-__global__ void __launch_bounds__(64) k_volsdf_step(const float* __restrict__ eu, const float* __restrict__ sdf, const float* __restrict__ beta0p,
-                                                    float* __restrict__ beta_io, int64_t R, int S, float eps, int beta_iters,
-                                                    float* __restrict__ weights, float* __restrict__ err_weights) {
-  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (r >= R) return;
+__global__ void __launch_bounds__(128) k_volsdf_step(const float* __restrict__ eu, const float* __restrict__ sdf, const float* __restrict__ beta0p,
+                                                     float* __restrict__ beta_io, int64_t R, int S, float eps, int beta_iters,
+                                                     float* __restrict__ weights, float* __restrict__ err_weights) {
+  extern __shared__ float vs_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+  if (r >= R) return;                                     // whole warp
+  float* delta_s = vs_smem + (size_t)wib * 3 * S;
+  float* dstar_s = delta_s + S;
+  float* sdf_s = dstar_s + S;
   const float* e = eu + r * (S + 1);
   const float* sd = sdf + r * S;
+  for (int i = lane; i < S; i += 32) {
+    delta_s[i] = __fsub_rn(e[i + 1], e[i]);
+    dstar_s[i] = volsdf_dstar(e, sd, i < S - 1 ? i : S - 2);
+    sdf_s[i] = sd[i];
+  }
+  __syncwarp();
   const float beta0 = *beta0p;
   float beta = beta_io[r];
   // get_updated_beta (:728-738)
-  if (volsdf_error_bound(e, sd, S, beta0) <= eps) beta = beta0;
+  if (volsdf_error_bound_warp(delta_s, dstar_s, sdf_s, S, beta0, lane) <= eps) beta = beta0;
   float bmin = beta0, bmax = beta;
   for (int j = 0; j < beta_iters; ++j) {
     const float mid = __fdiv_rn(__fadd_rn(bmin, bmax), 2.0f);
-    const float err = volsdf_error_bound(e, sd, S, mid);
+    const float err = volsdf_error_bound_warp(delta_s, dstar_s, sdf_s, S, mid, lane);
     if (err <= eps) bmax = mid;
     if (err > eps) bmin = mid;
   }
   beta = bmax;
-  beta_io[r] = beta;
+  if (lane == 0) beta_io[r] = beta;
   // density weights + transmittance (rays.py:167-192) and the error-bound pdf (:664-671)
-  double integ = 0.0, errint = 0.0;
+  double carryE = 0.0, carryI = 0.0;
   const float b2 = __fmul_rn(4.0f, __fmul_rn(beta, beta));
-  for (int i = 0; i < S; ++i) {
-    const float delta = __fsub_rn(e[i + 1], e[i]);
-    const float dd = __fmul_rn(delta, laplace_density(sd[i], beta));
-    const float trans = expf(-(float)integ);
-    weights[r * S + i] = __fmul_rn(__fsub_rn(1.0f, expf(-dd)), trans);
-    const float ds = volsdf_dstar(e, sd, i < S - 1 ? i : S - 2);
-    const float err_sec = __fdiv_rn(__fmul_rn(expf(__fdiv_rn(-ds, beta)), __fmul_rn(delta, delta)), b2);
-    errint += (double)err_sec;
-    err_weights[r * S + i] = __fmul_rn(__fsub_rn(fminf(expf((float)errint), 1.0e6f), 1.0f), trans);
-    integ += (double)dd;
+  for (int s0 = 0; s0 < S; s0 += 32) {
+    const int i = s0 + lane;
+    const bool on = i < S;
+    const float delta = on ? delta_s[i] : 0.f;
+    const float dd = on ? __fmul_rn(delta, laplace_density(sdf_s[i], beta)) : 0.f;
+    const float err_sec = on ? __fdiv_rn(__fmul_rn(expf(__fdiv_rn(-dstar_s[i], beta)), __fmul_rn(delta, delta)), b2) : 0.f;
+    const double einc = warp_scan_incl((double)err_sec, lane);
+    const double iinc = warp_scan_incl((double)dd, lane);
+    const float trans = expf(-(float)(carryI + iinc - (double)dd));
+    if (on) {
+      weights[r * S + i] = __fmul_rn(__fsub_rn(1.0f, expf(-dd)), trans);
+      err_weights[r * S + i] = __fmul_rn(__fsub_rn(fminf(expf((float)(carryE + einc)), 1.0e6f), 1.0f), trans);
+    }
+    carryE += __shfl_sync(0xffffffffu, einc, 31);
+    carryI += __shfl_sync(0xffffffffu, iinc, 31);
   }
 }
 
@@ -396,8 +434,11 @@ extern "C" int sdfb200_volsdf_step(const float* euclid_bins, const float* sdf, c
   SDFB_REQUIRE(n_rays >= 0 && n_samples >= 2 && beta_iters >= 0, "bad sizes");
   if (n_rays == 0) return 0;
   SDFB_REQUIRE(euclid_bins && sdf && beta0 && beta && weights && err_weights, "NULL pointer");
-  k_volsdf_step<<<(unsigned)ceil_div(n_rays, 64), 64, 0, ST(stream)>>>(euclid_bins, sdf, beta0, beta, n_rays, n_samples, eps, beta_iters, weights,
-                                                                       err_weights);
+  SDFB_REQUIRE(n_samples <= kVolsdfMaxS, "volsdf_step: n_samples > 1000");
+  // one warp per ray, 4 rays per block; per-ray cache of delta / d* / sdf in shared memory
+  const size_t smem = (size_t)4 * 3 * n_samples * sizeof(float);
+  k_volsdf_step<<<(unsigned)ceil_div(n_rays, 4), 128, smem, ST(stream)>>>(euclid_bins, sdf, beta0, beta, n_rays, n_samples, eps, beta_iters, weights,
+                                                                          err_weights);
   SDFB_LAUNCHED("k_volsdf_step");
   return 0;
 }

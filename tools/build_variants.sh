@@ -4,10 +4,10 @@
 set -e
 cd "$(dirname "$0")/../sdfstudio_b200"
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr"
-OBJS=$(ls build/*.o | grep -v "field_tc" )
+OBJS=$(ls build/*.o | grep -v "field_tc_p2_torch\|field_tc_v\|tc_test" )
 for spec in "$@"; do
   name="${spec%%:*}"; defs="${spec#*:}"
-  /usr/local/cuda/bin/nvcc $FLAGS -DSDFB200_TC_TIMING $defs -c csrc/field_tc.cu -o build/field_tc_v$name.o &
+  /usr/local/cuda/bin/nvcc $FLAGS -DSDFB200_TC_TIMING $defs -c csrc/field_tc_p2_torch.cu -o build/field_tc_v$name.o &
 done
 wait
 for spec in "$@"; do

@@ -30,11 +30,11 @@ def main():
     spec = FieldSpec(num_layers=2, num_layers_color=2, hidden_dim=256, use_grid_feature=True, grid_layout="torch")
     sd = {k: v.detach().to(dev) for k, v in field.state_dict().items()}
     sd["hash_table"] = sd.pop("encoding.hash_table")
-    oracle = OracleField(spec, sd)
     R, S = args.rays, 128
     o, d, cam, nears, fars = (t.to(dev) for t in dtu_like_rays(R, 1000))
+    torch.set_default_device(dev)      # the oracle creates its constants with the default device (it is written for the CPU)
+    oracle = OracleField(spec, sd)
     white = torch.ones(3, device=dev)
-
     def step():
         b = samplers.spaced_sampler(nears, fars, S, "uniform")
         out = oracle.get_outputs(o, d, b.starts, b.deltas, cam, return_alphas=True)
