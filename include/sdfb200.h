@@ -285,6 +285,14 @@ int sdfb200_field_render(const sdfb200_field_t* f, const void* packed, const voi
                          const sdfb200_field_out_t* sample_out, const sdfb200_field_render_t* render, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* packed samples (the `ray_indices` / `num_rays` branch of the renderers, fed by nerfacc-style samplers: renderers.py:74-79 RGB,
+ * :192-194 accumulation, :249-253 expected depth; nerfacc.accumulate_along_rays == per-ray scatter-add): weights [N], rgb / normals
+ * [N,3], starts / ends [N] (frustum bin edges, for the depth), ray_indices [N] int64 in [0, n_rays).  Background COLOR or PER_RAY
+ * ('last_sample' is rejected like the reference does).  workspace >= n_rays * 8 floats.  out.depth is the un-clipped expected depth;
+ * out.steps_minmax (optional, pre-set to {+inf,-inf}) receives steps.min()/max() for sdfb200_depth_clip. */
+int sdfb200_render_packed(const float* weights, const float* rgb, const float* normals, const float* starts, const float* ends,
+                          const int64_t* ray_indices, int64_t n_samples_total, int64_t n_rays, const float* bg, int32_t bg_mode, int32_t clamp01,
+                          const sdfb200_render_out_t* out, void* workspace, size_t workspace_bytes, void* stream);
 /* torch.clip(depth, steps.min(), steps.max()) (:257) using the min/max accumulated by sdfb200_render. */
 int sdfb200_depth_clip(float* depth, const float* steps_minmax, int64_t n_rays, void* stream);
 

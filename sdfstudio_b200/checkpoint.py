@@ -47,3 +47,27 @@ def load_field_checkpoint(field, loaded_state, prefix: str = FIELD_PREFIX, stric
     if strict and (missing or unexpected):
         raise RuntimeError(f"checkpoint does not match the field: missing {missing}, unexpected {list(unexpected)}")
     return missing, list(unexpected)
+
+
+def load_density_field_checkpoint(density_field, loaded_state, index: int = 0, strict: bool = True):
+    """Load ``_model.proposal_networks.{index}.mlp_base.params`` (tiny-cuda-nn ``NetworkWithInputEncoding``: FullyFusedMLP weights then the
+    HashGrid table, nerfstudio/fields/density_fields.py:89-96) of a reference neus-facto / bakedsdf checkpoint into a
+    ``sdfstudio_b200.HashMLPDensityField``.  The vector length is checked (the output layer is stored 16 rows wide like tcnn pads it); the
+    ordering inside the vector follows tcnn's published layout (UNPINNED: tcnn is not vendored in the reference)."""
+    if isinstance(loaded_state, (str, bytes)) or hasattr(loaded_state, "__fspath__"):
+        loaded_state = torch.load(loaded_state, map_location="cpu")
+    sd = extract_state(loaded_state, f"_model.proposal_networks.{index}.")
+    key = "mlp_base.params"
+    if key not in sd:
+        raise KeyError(f"{key} not found under _model.proposal_networks.{index}.")
+    flat = sd[key].reshape(-1).to(torch.float32)
+    nb = density_field.mlp_base
+    if flat.numel() != nb.params.numel():
+        raise ValueError(f"mlp_base.params has {flat.numel()} entries, this proposal network needs {nb.params.numel()} "
+                         "(check num_levels / log2_hashmap_size / max_res / hidden_dim / num_layers)")
+    with torch.no_grad():
+        nb.params.copy_(flat.to(nb.params.device))
+    extra = [k for k in sd if k not in (key, "aabb")]
+    if strict and extra:
+        raise RuntimeError(f"unexpected entries for the proposal network: {extra}")
+    return [], extra

@@ -175,6 +175,61 @@ __global__ void __launch_bounds__(256) k_render_alphas(const RenderAlphaArgs a) 
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// packed samples (the nerfacc branch of the renderers: renderers.py:74-79,192-194,249-253): samples of all rays in one flat
+// list with a ray index each; nerfacc.accumulate_along_rays == scatter-add per ray.  Pass 1 accumulates, pass 2 finalises.
+// -----------------------------------------------------------------------------------------------------------------
+struct PackedArgs {
+  const float* weights; const float* rgb; const float* normals; const float* starts; const float* ends; const int64_t* ray_indices;
+  int64_t N, R;
+  float* acc;  // [R][8]: sum w, sum w rgb (3), sum w step, sum w n (3)
+  float* o_minmax;
+};
+__global__ void __launch_bounds__(256) k_render_packed_accumulate(const PackedArgs a) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  float smin = INFINITY, smax = -INFINITY;
+  if (i < a.N) {
+    const int64_t r = a.ray_indices[i];
+    if (r >= 0 && r < a.R) {
+      const float w = a.weights[i];
+      float* o = a.acc + r * 8;
+      atomicAdd(o, w);
+      if (a.rgb) { atomicAdd(o + 1, w * a.rgb[i * 3]); atomicAdd(o + 2, w * a.rgb[i * 3 + 1]); atomicAdd(o + 3, w * a.rgb[i * 3 + 2]); }
+      if (a.starts) {
+        const float step = __fdiv_rn(__fadd_rn(a.starts[i], a.ends[i]), 2.0f);
+        atomicAdd(o + 4, w * step);
+        smin = smax = step;
+      }
+      if (a.normals) { atomicAdd(o + 5, w * a.normals[i * 3]); atomicAdd(o + 6, w * a.normals[i * 3 + 1]); atomicAdd(o + 7, w * a.normals[i * 3 + 2]); }
+    }
+  }
+  if (a.o_minmax && a.starts) {
+    for (int s = 16; s > 0; s >>= 1) {
+      smin = fminf(smin, __shfl_xor_sync(0xffffffffu, smin, s));
+      smax = fmaxf(smax, __shfl_xor_sync(0xffffffffu, smax, s));
+    }
+    if ((threadIdx.x & 31) == 0 && smin <= smax) { atomic_min_float(a.o_minmax, smin); atomic_max_float(a.o_minmax + 1, smax); }
+  }
+}
+__global__ void k_render_packed_finish(const float* __restrict__ acc, int64_t R, const float* __restrict__ bg, int bg_mode, int clamp01, float* o_rgb,
+                                       float* o_depth, float* o_normal, float* o_acc) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float* a = acc + r * 8;
+  const float w = a[0];
+  if (o_rgb) {
+    const float* b = bg_mode == SDFB200_BG_PER_RAY ? bg + r * 3 : bg;
+    const float rem = 1.0f - w;
+    for (int c = 0; c < 3; ++c) {
+      const float v = a[1 + c] + b[c] * rem;
+      o_rgb[r * 3 + c] = clamp01 ? fminf(fmaxf(v, 0.f), 1.f) : v;
+    }
+  }
+  if (o_acc) o_acc[r] = w;
+  if (o_depth) o_depth[r] = a[4] / (w + 1e-10f);
+  if (o_normal) { o_normal[r * 3] = a[5]; o_normal[r * 3 + 1] = a[6]; o_normal[r * 3 + 2] = a[7]; }
+}
+
 __global__ void k_depth_clip(float* __restrict__ depth, const float* __restrict__ mm, int64_t R) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r < R) depth[r] = fminf(fmaxf(depth[r], mm[0]), mm[1]);
@@ -245,5 +300,31 @@ extern "C" int sdfb200_render_alphas(const float* alphas, const float* rgb, cons
   a.o_acc = out->accumulation; a.o_bgT = bg_transmittance; a.o_minmax = out->steps_minmax;
   k_render_alphas<<<(unsigned)ceil_div(n_rays, 8), 256, 0, (cudaStream_t)stream>>>(a);
   SDFB_LAUNCHED("k_render_alphas");
+  return 0;
+}
+
+extern "C" int sdfb200_render_packed(const float* weights, const float* rgb, const float* normals, const float* starts, const float* ends,
+                                     const int64_t* ray_indices, int64_t n_samples_total, int64_t n_rays, const float* bg, int32_t bg_mode, int32_t clamp01,
+                                     const sdfb200_render_out_t* out, void* workspace, size_t workspace_bytes, void* stream) {
+  SDFB_REQUIRE(n_samples_total >= 0 && n_rays >= 0, "bad sizes");
+  SDFB_REQUIRE(out != nullptr, "NULL pointer");
+  if (n_rays == 0) return 0;
+  SDFB_REQUIRE(workspace != nullptr && workspace_bytes >= (size_t)n_rays * 8 * sizeof(float), "render_packed: workspace must hold 8 floats per ray");
+  SDFB_REQUIRE(n_samples_total == 0 || (weights && ray_indices), "NULL pointer");
+  SDFB_REQUIRE(bg_mode != SDFB200_BG_LAST_SAMPLE, "background 'last_sample' is not defined for packed samples (renderers.py:76-77)");
+  if (out->rgb) SDFB_REQUIRE(rgb != nullptr && bg != nullptr, "rgb output needs rgb and background");
+  if (out->depth) SDFB_REQUIRE(starts != nullptr && ends != nullptr, "depth output needs starts and ends");
+  if (out->normal) SDFB_REQUIRE(normals != nullptr, "normal output needs normals");
+  SDFB_CUDA(cudaMemsetAsync(workspace, 0, (size_t)n_rays * 8 * sizeof(float), (cudaStream_t)stream));
+  PackedArgs a;
+  a.weights = weights; a.rgb = out->rgb ? rgb : nullptr; a.normals = out->normal ? normals : nullptr; a.starts = out->depth ? starts : nullptr; a.ends = ends;
+  a.ray_indices = ray_indices; a.N = n_samples_total; a.R = n_rays; a.acc = (float*)workspace; a.o_minmax = out->steps_minmax;
+  if (n_samples_total > 0) {
+    k_render_packed_accumulate<<<(unsigned)ceil_div(n_samples_total, 256), 256, 0, (cudaStream_t)stream>>>(a);
+    SDFB_LAUNCHED("k_render_packed_accumulate");
+  }
+  k_render_packed_finish<<<(unsigned)ceil_div(n_rays, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, n_rays, bg, bg_mode, clamp01, out->rgb,
+                                                                                             out->depth, out->normal, out->accumulation);
+  SDFB_LAUNCHED("k_render_packed_finish");
   return 0;
 }

@@ -3,9 +3,11 @@ neus-facto / bakedsdf, density_fields.py:40-121): same constructor, ``get_densit
 ``tcnn.NetworkWithInputEncoding`` (HashGrid + FullyFusedMLP, ReLU, no biases, output activation None) and applies
 ``trunc_exp``; here one fused kernel (sdfb200_density_field_forward) does lookup + MLP + exp.
 
-Parameters: ``mlp_base.params`` is ONE flat fp32 tensor like tcnn's: network weights first ([hidden, in_pad], hidden x hidden
-blocks, [hidden] output row; in_pad = L*F rounded up to 16), then the grid table in tcnn level layout.  tiny-cuda-nn is not
-vendored in the reference, so bit-compatibility of this ordering with a tcnn checkpoint is UNPINNED.
+Parameters: ``mlp_base.params`` is ONE flat fp32 tensor like tcnn's ``NetworkWithInputEncoding``: network weights first (row-major
+[hidden, in_pad], (n_hidden - 1) x [hidden, hidden], output matrix [16, hidden] = the single output neuron padded to tcnn's 16-row
+granularity, row 0 live; in_pad = L*F rounded up to 16), then the grid table in tcnn level layout -- so the element count equals a
+reference ``proposal_networks.{i}.mlp_base.params`` and ``checkpoint.load_density_field_checkpoint`` can load it.  tiny-cuda-nn is not
+vendored in the reference, so the ORDERING inside that vector is restated from tcnn's published layout and is UNPINNED.
 """
 import math
 from typing import Optional
@@ -72,7 +74,8 @@ class _NetworkWithInputEncoding(nn.Module):
         self.in_dim = n_levels * n_features
         self.in_pad = (self.in_dim + 15) // 16 * 16
         self.desc = make_grid_desc("tcnn", n_levels, n_features, log2_hashmap_size, base_res, per_level_scale, False)
-        self.n_net = hidden_dim * self.in_pad + (n_hidden_layers - 1) * hidden_dim * hidden_dim + hidden_dim
+        self.n_out_pad = 16                                   # tcnn pads the output layer to 16 neurons
+        self.n_net = hidden_dim * self.in_pad + (n_hidden_layers - 1) * hidden_dim * hidden_dim + self.n_out_pad * hidden_dim
         self.n_grid = self.desc._total_entries * n_features
         g = torch.Generator().manual_seed(seed)
         # tcnn: xavier-uniform weights, U(-1e-4, 1e-4) grid
@@ -81,7 +84,9 @@ class _NetworkWithInputEncoding(nn.Module):
         ws = [w0.reshape(-1)]
         for _ in range(n_hidden_layers - 1):
             ws.append(((torch.rand(hidden_dim, hidden_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (2 * hidden_dim))).reshape(-1))
-        ws.append((torch.rand(hidden_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (hidden_dim + 16)))
+        wo = torch.zeros(self.n_out_pad, hidden_dim)
+        wo[0] = (torch.rand(hidden_dim, generator=g) * 2 - 1) * math.sqrt(6.0 / (hidden_dim + 16))
+        ws.append(wo.reshape(-1))
         grid = (torch.rand(self.n_grid, generator=g) * 2 - 1) * 1e-4
         self.params = nn.Parameter(torch.cat(ws + [grid]))
 

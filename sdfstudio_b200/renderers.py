@@ -116,8 +116,51 @@ def _render(weights, rgb=None, normals=None, bins=None, background=None, clamp01
     return res
 
 
+def _render_packed(weights, ray_indices, num_rays, rgb=None, normals=None, ray_samples=None, background=None, clamp01=False, want_acc=False,
+                   want_normal=False, want_depth=False):
+    """packed-sample branch (samples of all rays in one flat list + ``ray_indices``; what nerfacc.accumulate_along_rays does in the
+    reference, renderers.py:74-79,192-194,249-253): one scatter-add launch + one per-ray finishing launch (sdfb200_render_packed)."""
+    lib = _lib.load()
+    w = _lib.f32c(weights.reshape(-1))
+    N, R = w.shape[0], int(num_rays)
+    dev = w.device
+    idx = ray_indices.reshape(-1).to(torch.int64).contiguous()
+    out = _lib.RenderOut()
+    res = {}
+    rgb_c = nrm_c = st = en = bg_t = None
+    bg_mode = _lib.BG_COLOR
+    if rgb is not None:
+        if isinstance(background, str) and background == "last_sample":
+            raise NotImplementedError("Background color 'last_sample' not implemented for packed samples.")
+        bg_mode, bg_t = _background(background, R, dev)
+        rgb_c = _lib.f32c(rgb.reshape(-1, 3))
+        res["rgb"] = torch.empty(R, 3, device=dev, dtype=torch.float32)
+        out.rgb = res["rgb"].data_ptr()
+    if want_normal:
+        nrm_c = _lib.f32c(normals.reshape(-1, 3))
+        res["normal"] = torch.empty(R, 3, device=dev, dtype=torch.float32)
+        out.normal = res["normal"].data_ptr()
+    if want_acc:
+        res["accumulation"] = torch.empty(R, device=dev, dtype=torch.float32)
+        out.accumulation = res["accumulation"].data_ptr()
+    if want_depth:
+        st, en = _lib.f32c(ray_samples.frustums.starts.reshape(-1)), _lib.f32c(ray_samples.frustums.ends.reshape(-1))
+        res["depth"] = torch.empty(R, device=dev, dtype=torch.float32)
+        mm = _minmax_init(dev)
+        out.depth, out.steps_minmax = res["depth"].data_ptr(), mm.data_ptr()
+    ws = torch.empty(max(R, 1) * 8, device=dev, dtype=torch.float32)
+    _lib.check(lib.sdfb200_render_packed(_lib.ptr(w), _lib.ptr(rgb_c), _lib.ptr(nrm_c), _lib.ptr(st), _lib.ptr(en), _lib.ptr(idx), N, R, _lib.ptr(bg_t), bg_mode,
+                                         int(clamp01), out, _lib.ptr(ws), ws.numel() * 4, _lib.stream_ptr()), "sdfb200_render_packed")
+    if want_depth:
+        _lib.check(lib.sdfb200_depth_clip(out.depth, out.steps_minmax, R, _lib.stream_ptr()), "sdfb200_depth_clip")
+        res["depth"] = res["depth"][:, None]
+    if want_acc:
+        res["accumulation"] = res["accumulation"][:, None]
+    return res
+
+
 class RGBRenderer(nn.Module):
-    """renderers.py:42-118 (``ray_indices`` / packed samples are out of scope)."""
+    """renderers.py:42-118, dense and packed (``ray_indices`` + ``num_rays``) branches."""
 
     def __init__(self, background_color: Union[str, torch.Tensor] = "random") -> None:
         super().__init__()
@@ -125,13 +168,13 @@ class RGBRenderer(nn.Module):
 
     @classmethod
     def combine_rgb(cls, rgb, weights, background_color="random", ray_indices=None, num_rays=None):
-        if ray_indices is not None:
-            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        if ray_indices is not None and num_rays is not None:
+            return _render_packed(weights, ray_indices, num_rays, rgb=rgb, background=background_color, clamp01=False)["rgb"]
         return _render(weights, rgb=rgb, background=background_color, clamp01=False)["rgb"]
 
     def forward(self, rgb, weights, ray_indices=None, num_rays=None):
-        if ray_indices is not None:
-            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        if ray_indices is not None and num_rays is not None:
+            return _render_packed(weights, ray_indices, num_rays, rgb=rgb, background=self.background_color, clamp01=not self.training)["rgb"]
         return _render(weights, rgb=rgb, background=self.background_color, clamp01=not self.training)["rgb"]
 
 
@@ -140,8 +183,8 @@ class AccumulationRenderer(nn.Module):
 
     @classmethod
     def forward(cls, weights, ray_indices=None, num_rays=None):
-        if ray_indices is not None:
-            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        if ray_indices is not None and num_rays is not None:
+            return _render_packed(weights, ray_indices, num_rays, want_acc=True)["accumulation"]
         return _render(weights, want_acc=True)["accumulation"]
 
 
@@ -155,8 +198,10 @@ class DepthRenderer(nn.Module):
         self.method = method
 
     def forward(self, weights, ray_samples, ray_indices=None, num_rays=None):
-        if ray_indices is not None:
-            raise NotImplementedError("packed samples (nerfacc branch) are out of scope")
+        if ray_indices is not None and num_rays is not None:
+            if self.method == "median":
+                raise NotImplementedError("Median depth calculation is not implemented for packed samples.")
+            return _render_packed(weights, ray_indices, num_rays, ray_samples=ray_samples, want_depth=True)["depth"]
         return _render(weights, bins=bins_of(ray_samples), depth_method=self.method)["depth"]
 
 

@@ -204,3 +204,25 @@ def test_spaced_sampler_accepts_the_reference_callables():
         sb.SpacedSampler(spacing_fn=lambda x: x**3, spacing_fn_inv=lambda x: x ** (1 / 3))
     with pytest.raises(ValueError):
         sb.SpacedSampler(spacing_fn=torch.sqrt, spacing_fn_inv=lambda x: x)
+
+
+def test_proposal_network_checkpoint_layout_loads():
+    """neus-facto / bakedsdf proposal networks (fields/density_fields.py:89-96): `mlp_base.params` of a trainer checkpoint loads; the MLP
+    part has tiny-cuda-nn's element count (output layer padded to 16 neurons)."""
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200 import checkpoint
+
+    aabb = torch.tensor([[-1.0, -1, -1], [1, 1, 1]])
+    src = sb.HashMLPDensityField(aabb, num_layers=2, hidden_dim=16, num_levels=5, max_res=64, log2_hashmap_size=12)
+    dst = sb.HashMLPDensityField(aabb, num_layers=2, hidden_dim=16, num_levels=5, max_res=64, log2_hashmap_size=12)
+    nb = src.mlp_base
+    assert nb.n_net == 16 * 16 + 16 * 16          # FullyFusedMLP(n_neurons 16, 1 hidden layer): [16, pad16(10)] + [16 (padded output), 16]
+    with torch.no_grad():
+        nb.params.copy_(torch.randn(nb.params.shape, generator=torch.Generator().manual_seed(4)))
+    ckpt = {"step": 1, "pipeline": {"module._model.proposal_networks.0.mlp_base.params": nb.params.detach().half(),      # tcnn stores fp16 or fp32
+                                    "module._model.proposal_networks.0.aabb": aabb, "module._model.field.laplace_density.beta": torch.ones(1)}}
+    checkpoint.load_density_field_checkpoint(dst, ckpt, index=0)
+    assert torch.equal(dst.mlp_base.params.detach(), nb.params.detach().half().float())
+    wrong = sb.HashMLPDensityField(aabb, num_layers=2, hidden_dim=16, num_levels=5, max_res=64, log2_hashmap_size=13)
+    with pytest.raises(ValueError):
+        checkpoint.load_density_field_checkpoint(wrong, ckpt, index=0)

@@ -415,3 +415,48 @@ def test_proposal_network_sampler_matches_oracle():
     torch.testing.assert_close(sb.rays.bins_of(rs_list[1]).cpu(), obl[1].euclid, rtol=0, atol=5e-3)
     torch.testing.assert_close(sb.rays.bins_of(rs).cpu(), ob.euclid, rtol=0, atol=2e-2)
     assert (sb.rays.bins_of(rs)[:, 1:] >= sb.rays.bins_of(rs)[:, :-1]).all()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# packed samples: the `ray_indices` / `num_rays` branch of the renderers (renderers.py:74-79,192-194,249-253)
+# ----------------------------------------------------------------------------------------------------------------
+def test_packed_renderers_match_dense_and_reference_formulas():
+    """A ragged packed sample list (different sample counts per ray, one ray with no sample) against (a) the fp64 restatement of
+    nerfacc.accumulate_along_rays = per-ray index_add and (b) the dense renderers on a zero-padded copy."""
+    import sdfstudio_b200 as sb
+
+    g = torch.Generator().manual_seed(17)
+    R, Smax = 301, 23
+    counts = torch.randint(0, Smax + 1, (R,), generator=g)
+    counts[5] = 0
+    N = int(counts.sum())
+    ray_indices = torch.repeat_interleave(torch.arange(R), counts)
+    w = torch.rand(N, 1, generator=g) * 0.2
+    rgb = torch.rand(N, 3, generator=g)
+    nrm = torch.randn(N, 3, generator=g)
+    starts = torch.rand(N, 1, generator=g) * 3 + 0.5
+    ends = starts + torch.rand(N, 1, generator=g) * 0.1
+    bg = torch.tensor([0.2, 0.7, 0.4])
+
+    class _Fr:
+        pass
+
+    class _RS:
+        frustums = _Fr()
+
+    _RS.frustums.starts, _RS.frustums.ends = starts.cuda(), ends.cuda()
+    o_rgb = sb.RGBRenderer(background_color=bg.cuda()).eval()(rgb.cuda(), w.cuda(), ray_indices=ray_indices.cuda(), num_rays=R)
+    o_acc = sb.AccumulationRenderer.forward(w.cuda(), ray_indices=ray_indices.cuda(), num_rays=R)
+    o_dep = sb.DepthRenderer("expected")(w.cuda(), _RS, ray_indices=ray_indices.cuda(), num_rays=R)
+    # (a) fp64 index_add
+    w64 = w.double()
+    acc = torch.zeros(R, 1, dtype=torch.float64).index_add_(0, ray_indices, w64)
+    crgb = torch.zeros(R, 3, dtype=torch.float64).index_add_(0, ray_indices, w64 * rgb.double()) + bg.double() * (1 - acc)
+    steps = (starts.double() + ends.double()) / 2
+    dep = (torch.zeros(R, 1, dtype=torch.float64).index_add_(0, ray_indices, w64 * steps) / (acc + 1e-10)).clip(steps.min(), steps.max())
+    torch.testing.assert_close(o_acc.cpu().double(), acc, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(o_rgb.cpu().double(), crgb.clamp(0, 1), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(o_dep.cpu().double(), dep, rtol=1e-5, atol=1e-5)
+    assert o_rgb.shape == (R, 3) and o_acc.shape == (R, 1) and o_dep.shape == (R, 1)
+    with pytest.raises(NotImplementedError):
+        sb.RGBRenderer(background_color="last_sample")(rgb.cuda(), w.cuda(), ray_indices=ray_indices.cuda(), num_rays=R)
