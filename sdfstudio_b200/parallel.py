@@ -33,6 +33,21 @@ def slice_ray_bundle(ray_bundle, s: int, e: int):
     return type(ray_bundle)(**{k: v for k, v in kw.items() if v is not None or k in ("directions_norm", "camera_indices", "nears", "fars")})
 
 
+def flatten_ray_bundle(ray_bundle):
+    """(flat bundle, image_shape | None).  The reference hands ``get_outputs_for_camera_ray_bundle`` a camera ray bundle of shape
+    [H, W] (every field [H, W, k]; models/base_model.py:165-189 flattens it chunk by chunk with get_row_major_sliced_ray_bundle);
+    a flat [N] bundle passes through unchanged."""
+    o = ray_bundle.origins
+    if o.dim() == 2:
+        return ray_bundle, None
+    image_shape = tuple(o.shape[:-1])
+    kw = {}
+    for name in ("origins", "directions", "pixel_area", "directions_norm", "camera_indices", "nears", "fars", "times"):
+        v = getattr(ray_bundle, name, None)
+        kw[name] = None if v is None else v.reshape(-1, v.shape[-1])
+    return type(ray_bundle)(**{k: v for k, v in kw.items() if v is not None or k in ("directions_norm", "camera_indices", "nears", "fars")}), image_shape
+
+
 def gather_outputs(outputs: Dict[str, torch.Tensor], n_rays: int, dst: int = 0) -> Optional[Dict[str, torch.Tensor]]:
     """Concatenate per-rank ray slices (in rank order) on `dst`; other ranks get None."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:

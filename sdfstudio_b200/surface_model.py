@@ -72,8 +72,13 @@ class SurfaceRenderer(nn.Module):
     @torch.no_grad()
     def get_outputs_for_camera_ray_bundle(self, camera_ray_bundle, keys=("rgb", "depth", "normal", "accumulation"),
                                           image_shape: Optional[tuple] = None, distributed: bool = False) -> Optional[Dict[str, torch.Tensor]]:
-        """base_model.py:165-189 with big chunks.  ``camera_ray_bundle``: flat [N] rays (row-major image order).  With
-        ``distributed=True`` every rank renders its contiguous slice and rank 0 gets the gathered image (others: None)."""
+        """base_model.py:165-189 with big chunks.  ``camera_ray_bundle``: the reference's [H, W] camera ray bundle (outputs come back
+        as [H, W, k] like ``outputs[name].view(image_height, image_width, -1)`` there) or flat [N] rays in row-major image order (then
+        ``image_shape`` optionally reshapes).  With ``distributed=True`` every rank renders its contiguous slice and rank 0 gets the
+        gathered image (others: None)."""
+        camera_ray_bundle, hw = parallel.flatten_ray_bundle(camera_ray_bundle)
+        if hw is not None and image_shape is None:
+            image_shape = hw
         n = camera_ray_bundle.origins.shape[0]
         bundle = camera_ray_bundle
         if distributed and parallel.dist.is_initialized() and parallel.dist.get_world_size() > 1:

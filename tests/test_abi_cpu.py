@@ -226,3 +226,42 @@ def test_proposal_network_checkpoint_layout_loads():
     wrong = sb.HashMLPDensityField(aabb, num_layers=2, hidden_dim=16, num_levels=5, max_res=64, log2_hashmap_size=13)
     with pytest.raises(ValueError):
         checkpoint.load_density_field_checkpoint(wrong, ckpt, index=0)
+
+
+@pytest.mark.reference
+def test_reference_tensordataclasses_pass_through_the_host_side():
+    """The reference's own RayBundle / RaySamples (TensorDataclass objects with expanded stride-0 fields, cameras/rays.py:233-339) are what the
+    modules receive inside sdfstudio: the host-side accessors must read them, keep their TYPE when slicing / flattening, and rebuild the
+    [R, S+1] bin buffer the kernels take.  Structure only (no kernel runs on the CPU box)."""
+    from oracle import ref_import
+
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200 import parallel
+
+    ref = ref_import.ref_modules()
+    H, W, S = 5, 7, 9
+    g = torch.Generator().manual_seed(2)
+    d = torch.randn(H, W, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    bundle = ref.RayBundle(origins=torch.randn(H, W, 3, generator=g), directions=d, pixel_area=torch.ones(H, W, 1), directions_norm=torch.ones(H, W, 1),
+                           camera_indices=torch.zeros(H, W, 1, dtype=torch.long), nears=torch.full((H, W, 1), 0.5), fars=torch.full((H, W, 1), 4.5))
+    flat, hw = parallel.flatten_ray_bundle(bundle)
+    assert hw == (H, W) and type(flat) is type(bundle) and flat.origins.shape == (H * W, 3) and flat.camera_indices.dtype == torch.long
+    assert torch.equal(flat.origins.view(H, W, 3), bundle.origins)
+    part = parallel.slice_ray_bundle(flat, 3, 11)
+    assert type(part) is type(bundle) and part.origins.shape == (8, 3) and torch.equal(part.fars, flat.fars[3:11])
+    sh = parallel.shard_ray_bundle(flat, 1, 3)
+    assert sh.origins.shape[0] == parallel.shard_bounds(H * W, 1, 3)[1] - parallel.shard_bounds(H * W, 1, 3)[0]
+    # the reference sampler's RaySamples: starts / ends are overlapping slices of one bin buffer, origins / directions stride-0 expanded
+    rs = ref.ray_samplers.UniformSampler(num_samples=S).eval()(flat)
+    assert rs.frustums.origins.stride()[1] == 0
+    bins = sb.rays.bins_of(rs)
+    assert bins.shape == (H * W, S + 1) and bins.is_contiguous()
+    assert torch.equal(bins[:, :-1], rs.frustums.starts[..., 0]) and torch.equal(bins[:, 1:], rs.frustums.ends[..., 0])
+    sp = sb.rays.spacing_bins_of(rs)
+    assert torch.equal(sp[:, :-1], rs.spacing_starts[..., 0]) and torch.equal(sp[:, -1], rs.spacing_ends[:, -1, 0])
+    o2, d2 = sb.rays.rays_of(rs)
+    assert o2.is_contiguous() and torch.equal(o2, flat.origins) and torch.equal(d2, flat.directions)
+    # FieldHeadNames of the reference compare equal to the product's keys (dicts returned by SDFField are indexed with either)
+    assert {h.value for h in ref.FieldHeadNames} >= {h.value for h in sb.FieldHeadNames} or all(
+        getattr(ref.FieldHeadNames, h.name).value == h.value for h in sb.FieldHeadNames)

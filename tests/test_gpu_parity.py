@@ -460,3 +460,36 @@ def test_packed_renderers_match_dense_and_reference_formulas():
     assert o_rgb.shape == (R, 3) and o_acc.shape == (R, 1) and o_dep.shape == (R, 1)
     with pytest.raises(NotImplementedError):
         sb.RGBRenderer(background_color="last_sample")(rgb.cuda(), w.cuda(), ray_indices=ray_indices.cuda(), num_rays=R)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# samplers driven by IDENTICAL sdf values (the oracle's, evaluated on the product's own sample positions): what remains is the
+# arithmetic of the sampler kernels themselves, so the bounds are tight (no field rounding to absorb)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["neusfacto_c1"])
+def test_samplers_on_shared_sdf_function(name):
+    import sdfstudio_b200 as sb
+
+    spec, kw, o, d, cam, nears, fars, oracle, field = build_case(name)
+    rb = make_bundle(o, d, cam, nears, fars)
+
+    def shared_sdf(rs):                                   # the ORACLE's fp32 sdf at the product's sample starts
+        starts = sb.rays.bins_of(rs)[:, :-1].cpu()
+        return oracle.get_sdf(o, d, starts).cuda()[..., None]
+
+    sdf32 = lambda starts: oracle.get_sdf(o, d, starts)  # noqa: E731
+    rs_n = sb.NeuSSampler().eval()(rb, sdf_fn=shared_sdf)
+    on = samplers.neus_sampler(nears, fars, sdf32)
+    pn = sb.rays.spacing_bins_of(rs_n).cpu()
+    # every upsampling round inverts a CDF: bins agree to a few ulp of the [0,1] spacing domain and the ORDER of the merged samples
+    # (the sorted_index stream of merge_ray_samples) is identical
+    assert float((pn - on.spacing).abs().max()) < 2e-6, float((pn - on.spacing).abs().max())
+    assert float((pn == on.spacing).float().mean()) > 0.9
+    assert torch.equal(torch.argsort(pn[:, :-1], dim=-1, stable=True), torch.argsort(on.spacing[:, :-1], dim=-1, stable=True))
+    rs_e = sb.ErrorBoundedSampler(num_samples=64, num_samples_eval=128, num_samples_extra=32).eval()(rb, density_fn=field.laplace_density, sdf_fn=shared_sdf,
+                                                                                                   return_eikonal_points=False)
+    oe = samplers.error_bounded_sampler(nears, fars, sdf32, oracle.get_beta())
+    pe = sb.rays.spacing_bins_of(rs_e).cpu()
+    assert pe.shape == oe.spacing.shape
+    assert float((pe - oe.spacing).abs().max()) < 5e-6, float((pe - oe.spacing).abs().max())
+    assert float((sb.rays.bins_of(rs_e).cpu() - oe.euclid).abs().max()) < 2e-5
