@@ -85,7 +85,7 @@ __global__ void k_pack_heads(const float* dw, const float* db, const float* tw, 
 }
 
 // -----------------------------------------------------------------------------------------------------------------
-// inputs: positions, contraction, PE.  One thread per point.
+// inputs: positions, contraction, PE.
 // -----------------------------------------------------------------------------------------------------------------
 struct InputArgs {
   const float* origins; const float* directions; const float* bins;
@@ -95,8 +95,12 @@ struct InputArgs {
   float* x; float* x01; float* in; float* points_norm; float* points_out;
 };
 
+// One WARP per point (8 points per block): lane l writes columns l, l+32, ... of the point's input row, so the 1.5 KB row leaves the
+// SM as coalesced 128-byte stores (a thread-per-point layout strides the lanes by the row length: 32 L1 wavefronts per store
+// instruction, and all of a row's sinf evaluations serialised in one thread).
 __global__ void __launch_bounds__(256) k_field_inputs(const InputArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= a.n_points) return;
   const int64_t gi = a.point0 + i;
   float px, py, pz;
@@ -119,27 +123,32 @@ __global__ void __launch_bounds__(256) k_field_inputs(const InputArgs a) {
       px = __fmul_rn(k, __fdiv_rn(px, mag)); py = __fmul_rn(k, __fdiv_rn(py, mag)); pz = __fmul_rn(k, __fdiv_rn(pz, mag));
     }
   }
-  if (a.points_norm) a.points_norm[gi] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
-  if (a.points_out) { a.points_out[gi * 3] = px; a.points_out[gi * 3 + 1] = py; a.points_out[gi * 3 + 2] = pz; }
+  if (lane == 0) {
+    if (a.points_norm) a.points_norm[gi] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
+    if (a.points_out) { a.points_out[gi * 3] = px; a.points_out[gi * 3 + 1] = py; a.points_out[gi * 3 + 2] = pz; }
+  }
   px += a.dx; py += a.dy; pz += a.dz;
-  a.x[i * 3] = px; a.x[i * 3 + 1] = py; a.x[i * 3 + 2] = pz;
-  a.x01[i * 3] = (px + 2.0f) * 0.25f; a.x01[i * 3 + 1] = (py + 2.0f) * 0.25f; a.x01[i * 3 + 2] = (pz + 2.0f) * 0.25f;
+  if (lane < 3) {
+    const float v = lane == 0 ? px : (lane == 1 ? py : pz);
+    a.x[i * 3 + lane] = v;
+    a.x01[i * 3 + lane] = (v + 2.0f) * 0.25f;
+  }
   float* row = a.in + i * a.in_pad;
-  row[0] = px; row[1] = py; row[2] = pz;
   const int nb = a.off_axis ? 21 : 3;
   const int half = nb * a.pe_degree;
-  for (int b = 0; b < nb; ++b) {
-    float v;
-    if (a.off_axis) v = offaxis_dot(px, py, pz, b);
-    else v = b == 0 ? px : (b == 1 ? py : pz);
-    float fr = 1.f;
-    for (int k = 0; k < a.pe_degree; ++k, fr *= 2.f) {
-      const float sarg = v * fr;
-      row[3 + b * a.pe_degree + k] = a.use_pe ? sinf(sarg) : 0.f;
-      row[3 + half + b * a.pe_degree + k] = a.use_pe ? sinf(sarg + kHalfPi) : 0.f;
+  for (int c = lane; c < a.in_pad; c += 32) {
+    float val = 0.f;                                       // grid block (overwritten by k_grid_encode) + padding
+    if (c < 3) val = c == 0 ? px : (c == 1 ? py : pz);
+    else if (c < 3 + a.pe_dim) {
+      const int j = c - 3;
+      const int jj = j >= half ? j - half : j;
+      const int b2 = jj / a.pe_degree, k = jj - b2 * a.pe_degree;
+      const float v = a.off_axis ? offaxis_dot(px, py, pz, b2) : (b2 == 0 ? px : (b2 == 1 ? py : pz));
+      const float sarg = v * (float)(1 << k);
+      val = a.use_pe ? sinf(j >= half ? sarg + kHalfPi : sarg) : 0.f;
     }
+    row[c] = val;
   }
-  for (int c = 3 + a.pe_dim; c < a.in_pad; ++c) row[c] = 0.f;  // grid block (overwritten by k_grid_encode) + pad
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -269,40 +278,45 @@ struct GradArgs {
   const float* gin; const float* in; const float* jac; int in_pad, pe_degree, use_pe, off_axis, pe_dim, grid_dim, use_grid;
   int64_t n; float* grad;
 };
+// one warp per point: lane l owns input columns l, l+32, ...; three warp reductions at the end
 __global__ void __launch_bounds__(256) k_grad_finish(const GradArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= a.n) return;
   const float* g = a.gin + i * a.in_pad;
   const float* in = a.in + i * a.in_pad;
-  float gx = g[0], gy = g[1], gz = g[2];
+  const float x0 = in[0], x1 = in[1], x2 = in[2];
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (lane < 3) { const float v = g[lane]; gx = lane == 0 ? v : 0.f; gy = lane == 1 ? v : 0.f; gz = lane == 2 ? v : 0.f; }
   if (a.use_pe) {
     const int nb = a.off_axis ? 21 : 3;
     const int half = nb * a.pe_degree;
-    for (int b = 0; b < nb; ++b) {
-      float v;
-      if (a.off_axis) v = offaxis_dot(in[0], in[1], in[2], b);
-      else v = in[b];
-      float acc = 0.f, fr = 1.f;
-      for (int k = 0; k < a.pe_degree; ++k, fr *= 2.f) {
-        const int c = 3 + b * a.pe_degree + k;
-        // autograd of sin(s) and sin(u), u = fl(s + pi/2): cos evaluated on the SAME fp32 arguments as the forward
-        const float sarg = v * fr;
-        acc += fr * (g[c] * cosf(sarg) + g[c + half] * cosf(sarg + kHalfPi));
-      }
-      if (a.off_axis) { gx += acc * c_offaxis[0][b]; gy += acc * c_offaxis[1][b]; gz += acc * c_offaxis[2][b]; }
-      else if (b == 0) gx += acc; else if (b == 1) gy += acc; else gz += acc;
+    for (int j = lane; j < a.pe_dim; j += 32) {
+      const int jj = j >= half ? j - half : j;
+      const int b = jj / a.pe_degree, k = jj - b * a.pe_degree;
+      const float v = a.off_axis ? offaxis_dot(x0, x1, x2, b) : (b == 0 ? x0 : (b == 1 ? x1 : x2));
+      const float fr = (float)(1 << k);
+      const float sarg = v * fr;
+      // autograd of sin(s) and sin(u), u = fl(s + pi/2): cos evaluated on the SAME fp32 arguments as the forward
+      const float t = fr * g[3 + j] * cosf(j >= half ? sarg + kHalfPi : sarg);
+      if (a.off_axis) { gx = fmaf(t, c_offaxis[0][b], gx); gy = fmaf(t, c_offaxis[1][b], gy); gz = fmaf(t, c_offaxis[2][b], gz); }
+      else if (b == 0) gx += t; else if (b == 1) gy += t; else gz += t;
     }
   }
   if (a.use_grid) {
     const float* J = a.jac + i * (int64_t)a.grid_dim * 3;
     float jx = 0.f, jy = 0.f, jz = 0.f;
-    for (int c = 0; c < a.grid_dim; ++c) {
+    for (int c = lane; c < a.grid_dim; c += 32) {
       const float gv = g[3 + a.pe_dim + c];
       jx = fmaf(gv, J[c * 3], jx); jy = fmaf(gv, J[c * 3 + 1], jy); jz = fmaf(gv, J[c * 3 + 2], jz);
     }
     gx += 0.25f * jx; gy += 0.25f * jy; gz += 0.25f * jz;  // positions = (x + 2) / 4   (sdf_field.py:384)
   }
-  a.grad[i * 3] = gx; a.grad[i * 3 + 1] = gy; a.grad[i * 3 + 2] = gz;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    gx += __shfl_xor_sync(0xffffffffu, gx, d); gy += __shfl_xor_sync(0xffffffffu, gy, d); gz += __shfl_xor_sync(0xffffffffu, gz, d);
+  }
+  if (lane == 0) { a.grad[i * 3] = gx; a.grad[i * 3 + 1] = gy; a.grad[i * 3 + 2] = gz; }
 }
 
 // numerical gradient from the 6 offset SDFs (sdf_field.py:446-453)
@@ -327,8 +341,11 @@ struct ColorInArgs {
   int64_t point0, n; int n_samples; int has_bins; int geo_feat, app_dim, use_diffuse, use_reflections, use_n_dot_v, cin_pad;
   float* cin;
 };
+// one warp per point: lane l writes columns l, l+32, ... of the colour-network input row (coalesced; the 256-wide geo feature copy
+// is a row-to-row copy)
 __global__ void __launch_bounds__(256) k_color_inputs(const ColorInArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= a.n) return;
   const int64_t gi = a.point0 + i;
   const int64_t r = a.has_bins ? gi / a.n_samples : gi;
@@ -343,26 +360,29 @@ __global__ void __launch_bounds__(256) k_color_inputs(const ColorInArgs a) {
     ex = dot * nx + dx; ey = dot * ny + dy; ez = dot * nz + dz;
   }
   float* row = a.cin + i * a.cin_pad;
-  int c = 0;
-  if (!a.use_diffuse) { row[0] = a.x[i * 3]; row[1] = a.x[i * 3 + 1]; row[2] = a.x[i * 3 + 2]; c = 3; }
-  const float e[3] = {ex, ey, ez};
-  for (int b = 0; b < 3; ++b) {
-    float fr = 1.f;
-    for (int k = 0; k < 4; ++k, fr *= 2.f) {
-      row[c + b * 4 + k] = sinf(e[b] * fr);
-      row[c + 12 + b * 4 + k] = sinf(e[b] * fr + kHalfPi);
-    }
-  }
-  row[c + 24] = ex; row[c + 25] = ey; row[c + 26] = ez;
-  c += 27;
-  if (!a.use_diffuse) { row[c] = gx; row[c + 1] = gy; row[c + 2] = gz; c += 3; }
+  const int c_enc = a.use_diffuse ? 0 : 3;                  // x(3) first unless the diffuse head is on
+  const int c_grad = c_enc + 27;                            // gradient(3) unless the diffuse head is on
+  const int c_gf = c_grad + (a.use_diffuse ? 0 : 3);
+  const int c_app = c_gf + a.geo_feat;
+  const int c_ndv = c_app + a.app_dim;
   const float* gf = a.outg + i * a.ldoutg + 1;
-  for (int k = 0; k < a.geo_feat; ++k) row[c + k] = gf[k];
-  c += a.geo_feat;
-  for (int k = 0; k < a.app_dim; ++k) row[c + k] = a.appearance ? __ldg(a.appearance + r * a.app_dim + k) : 0.f;
-  c += a.app_dim;
-  if (a.use_n_dot_v) row[c++] = nx * dx + ny * dy + nz * dz;
-  for (; c < a.cin_pad; ++c) row[c] = 0.f;
+  for (int c = lane; c < a.cin_pad; c += 32) {
+    float val = 0.f;
+    if (c < c_enc) val = a.x[i * 3 + c];
+    else if (c < c_enc + 24) {
+      const int j = c - c_enc;
+      const int jj = j >= 12 ? j - 12 : j;
+      const int b = jj >> 2, k = jj & 3;
+      const float e = b == 0 ? ex : (b == 1 ? ey : ez);
+      const float arg = e * (float)(1 << k);
+      val = sinf(j >= 12 ? arg + kHalfPi : arg);
+    } else if (c < c_enc + 27) { const int j = c - c_enc - 24; val = j == 0 ? ex : (j == 1 ? ey : ez); }
+    else if (c < c_gf) { const int j = c - c_grad; val = j == 0 ? gx : (j == 1 ? gy : gz); }
+    else if (c < c_app) val = gf[c - c_gf];
+    else if (c < c_ndv) val = a.appearance ? __ldg(a.appearance + r * a.app_dim + (c - c_app)) : 0.f;
+    else if (c == c_ndv && a.use_n_dot_v) val = nx * dx + ny * dy + nz * dz;
+    row[c] = val;
+  }
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -374,16 +394,35 @@ struct PostArgs {
   const float* variance; const float* beta; const float* beta_min; float cos_anneal;
   float *sdf, *geo_feature, *gradients, *normals, *rgb, *density, *alpha, *occupancy;
 };
+// one warp per point: the geo-feature copy and the six 256-wide head dot products (diffuse / tint, sdf_field.py:596-607) are split over
+// the lanes; the scalar heads are finished by lane 0
 __global__ void __launch_bounds__(256) k_field_post(const PostArgs a) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= a.n) return;
   const int64_t gi = a.point0 + i;
   const float sdf = a.outg[i * a.ldoutg];
-  if (a.sdf) a.sdf[gi] = sdf;
-  if (a.geo_feature) {
-    const float* gf = a.outg + i * a.ldoutg + 1;
-    for (int k = 0; k < a.geo_feat; ++k) a.geo_feature[gi * a.geo_feat + k] = gf[k];
+  const float* gf = a.outg + i * a.ldoutg + 1;
+  if (a.geo_feature)
+    for (int k = lane; k < a.geo_feat; k += 32) a.geo_feature[gi * a.geo_feat + k] = gf[k];
+  float hd[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (a.rgb && a.use_diffuse) {
+    const int per = 3 * a.geo_feat + 4;
+    for (int k = lane; k < a.geo_feat; k += 32) {
+      const float f = gf[k];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        hd[c] = fmaf(__ldg(a.heads + c * a.geo_feat + k), f, hd[c]);
+        if (a.use_tint) hd[3 + c] = fmaf(__ldg(a.heads + per + c * a.geo_feat + k), f, hd[3 + c]);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+#pragma unroll
+      for (int c = 0; c < 6; ++c) hd[c] += __shfl_xor_sync(0xffffffffu, hd[c], d);
   }
+  if (lane != 0) return;
+  if (a.sdf) a.sdf[gi] = sdf;
   float gx = 0.f, gy = 0.f, gz = 0.f;
   if (a.grad) { gx = a.grad[i * 3]; gy = a.grad[i * 3 + 1]; gz = a.grad[i * 3 + 2]; }
   if (a.gradients) { a.gradients[gi * 3] = gx; a.gradients[gi * 3 + 1] = gy; a.gradients[gi * 3 + 2] = gz; }
@@ -396,24 +435,11 @@ __global__ void __launch_bounds__(256) k_field_post(const PostArgs a) {
     for (int c = 0; c < 3; ++c) rgb[c] = sigmoidf_(a.craw[i * a.ldc + c]);
     if (a.use_diffuse) {
       // sdf_field.py:596-607
-      const float* gf = a.outg + i * a.ldoutg + 1;
       const int per = 3 * a.geo_feat + 4;
       for (int c = 0; c < 3; ++c) {
-        const float* wd = a.heads + c * a.geo_feat;
-        float rd = 0.f;
-        for (int k = 0; k < a.geo_feat; ++k) rd = fmaf(__ldg(wd + k), gf[k], rd);
-        rd += a.heads[3 * a.geo_feat + c];
+        const float rd = hd[c] + a.heads[3 * a.geo_feat + c];
         const float diffuse = sigmoidf_(rd - 1.0986122886681098f);  // log(3)
-        float spec;
-        if (a.use_tint) {
-          const float* wt = a.heads + per + c * a.geo_feat;
-          float rt = 0.f;
-          for (int k = 0; k < a.geo_feat; ++k) rt = fmaf(__ldg(wt + k), gf[k], rt);
-          rt += a.heads[per + 3 * a.geo_feat + c];
-          spec = sigmoidf_(rt) * rgb[c];
-        } else {
-          spec = 0.5f * rgb[c];
-        }
+        const float spec = a.use_tint ? sigmoidf_(hd[3 + c] + a.heads[per + 3 * a.geo_feat + c]) * rgb[c] : 0.5f * rgb[c];
         rgb[c] = fminf(fmaxf(spec + diffuse, 0.f), 1.f);
       }
     }
@@ -582,6 +608,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
   for (int64_t p0 = 0; p0 < N; p0 += chunk) {
     const int64_t n = (N - p0) < chunk ? (N - p0) : chunk;
     const unsigned pb = (unsigned)ceil_div(n, 256);
+    const unsigned wb = (unsigned)ceil_div(n, 8);     // warp-per-point kernels: 8 points per 256-thread block
     InputArgs ia;
     ia.origins = in.origins; ia.directions = in.directions; ia.bins = in.bins; ia.point0 = p0; ia.n_points = n; ia.n_samples = in.n_samples;
     ia.contraction = in.apply_contraction ? f.contraction : SDFB200_CONTRACT_NONE;
@@ -597,7 +624,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
         InputArgs ib = ia;
         ib.dx = offs[k][0]; ib.dy = offs[k][1]; ib.dz = offs[k][2];
         ib.points_norm = nullptr; ib.points_out = nullptr;
-        k_field_inputs<<<pb, 256, 0, st>>>(ib);
+        k_field_inputs<<<wb, 256, 0, st>>>(ib);
         SDFB_LAUNCHED("k_field_inputs");
         if (use_grid) {
           int r = grid_encode(f.grid, table, ws + w.x01, n, ws + w.in + 3 + p.pe_dim, p.in_pad, nullptr, st);
@@ -612,7 +639,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
       SDFB_LAUNCHED("k_numgrad");
       if (out.sampled_sdf) SDFB_CUDA(cudaMemcpyAsync(out.sampled_sdf + p0 * 6, ws + w.nsdf, (size_t)n * 6 * 4, cudaMemcpyDeviceToDevice, st));
     }
-    k_field_inputs<<<pb, 256, 0, st>>>(ia);
+    k_field_inputs<<<wb, 256, 0, st>>>(ia);
     SDFB_LAUNCHED("k_field_inputs");
     const bool analytic = want_grad && !numerical;
     if (use_grid) {
@@ -627,7 +654,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
       GradArgs ga;
       ga.gin = ws + w.gin; ga.in = ws + w.in; ga.jac = ws + w.jac; ga.in_pad = p.in_pad; ga.pe_degree = f.pe_degree; ga.use_pe = f.use_position_encoding;
       ga.off_axis = f.off_axis; ga.pe_dim = p.pe_dim; ga.grid_dim = p.grid_dim; ga.use_grid = use_grid; ga.n = n; ga.grad = ws + w.grad;
-      k_grad_finish<<<pb, 256, 0, st>>>(ga);
+      k_grad_finish<<<wb, 256, 0, st>>>(ga);
       SDFB_LAUNCHED("k_grad_finish");
     }
     const float* craw = nullptr;
@@ -638,7 +665,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
       ca.appearance = in.appearance; ca.point0 = p0; ca.n = n; ca.n_samples = in.n_samples; ca.has_bins = in.bins != nullptr; ca.geo_feat = p.geo_feat;
       ca.app_dim = f.appearance_dim; ca.use_diffuse = f.use_diffuse_color; ca.use_reflections = f.use_reflections; ca.use_n_dot_v = f.use_n_dot_v;
       ca.cin_pad = p.cin_pad; ca.cin = ws + w.cin;
-      k_color_inputs<<<pb, 256, 0, st>>>(ca);
+      k_color_inputs<<<wb, 256, 0, st>>>(ca);
       SDFB_LAUNCHED("k_color_inputs");
       const float* X = ws + w.cin;
       int ldx = p.cin_pad;
@@ -660,7 +687,7 @@ int field_forward_fp32(const sdfb200_field_t& f, const FieldPlan& p, const char*
     pa.rgb_padding = f.rgb_padding; pa.variance = in.variance; pa.beta = in.beta; pa.beta_min = in.beta_min; pa.cos_anneal = in.cos_anneal_ratio;
     pa.sdf = out.sdf; pa.geo_feature = out.geo_feature; pa.gradients = out.gradients; pa.normals = out.normals; pa.rgb = out.rgb; pa.density = out.density;
     pa.alpha = out.alpha; pa.occupancy = out.occupancy;
-    k_field_post<<<pb, 256, 0, st>>>(pa);
+    k_field_post<<<wb, 256, 0, st>>>(pa);
     SDFB_LAUNCHED("k_field_post");
   }
   return 0;
