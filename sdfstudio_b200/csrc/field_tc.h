@@ -9,7 +9,10 @@ namespace sdfb200 {
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kGatherWarps = 4;                              // hash-grid part of the encode: one thread per point
-constexpr int kAluWarps = 2;                                 // PE / x / static colour columns: one thread per two points
+#ifndef TCV_ALU_WARPS
+#define TCV_ALU_WARPS 2
+#endif
+constexpr int kAluWarps = TCV_ALU_WARPS;                     // 0: the gather warps also write the PE / x / static colour columns; 2: two extra warps do (two points per thread)
 constexpr int kEncWarps = kGatherWarps + kAluWarps;
 constexpr int kWarpProducer = kEpiWarps + kEncWarps;         // 14
 constexpr int kWarpMma = kWarpProducer + 1;                  // 15

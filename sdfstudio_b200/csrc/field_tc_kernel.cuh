@@ -253,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     mbar_init(&g0done, 1);
     mbar_init(&a_ready, 2 * kEpiWarps);
     mbar_init(&in_ready, 2 * kEncWarps);
-    mbar_init(&misc_ready, 2 * kAluWarps);
+    mbar_init(&misc_ready, 2 * (kAluWarps > 0 ? kAluWarps : kGatherWarps));
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc2<512>(&tmem_base_s);
@@ -373,13 +373,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
   } else if (warp >= kEpiWarps) {
     // ============================== encode warps, one tile ahead of the compute warps ==============================
     // warps 8-11: hash gathers (one thread per point); warps 12-13: PE / x columns and the static colour columns (two points per thread)
-    const bool alu = warp >= kEpiWarps + kGatherWarps;
+    // (kAluWarps == 0: the four gather warps do all of it, one point per thread -- the PE / colour ALU work then spreads evenly over the
+    //  four SM sub-partitions instead of slowing down the epilogue warps that share a scheduler with the two extra warps)
+    const bool alu = kAluWarps > 0 && warp >= kEpiWarps + kGatherWarps;
     const int row = alu ? (warp - kEpiWarps - kGatherWarps) * 32 + lane : (warp - kEpiWarps) * 32 + lane;
     uint8_t* enc_s = reinterpret_cast<uint8_t*>(a.scratch + (size_t)blockIdx.x * a.scratch_per_cta) + 65536 + (size_t)P * 65536;
     const uint64_t pol_table = l2_policy(TCV_POL_TABLE);
     auto encode = [&](int tile, uint8_t* inA, uint8_t* enc) {
       if (alu) { encode_tile_pe<P>(a, tile, row, inA, enc); encode_tile_pe<P>(a, tile, row + 64, inA, enc); }
-      else encode_tile_grid<P, LAYOUT>(a, tile, row, inA, enc, pol_table);
+      else {
+        encode_tile_grid<P, LAYOUT>(a, tile, row, inA, enc, pol_table);
+        if (kAluWarps == 0) encode_tile_pe<P>(a, tile, row, inA, enc);
+      }
       fence_async_smem();
       __threadfence_block();
       __syncwarp();
@@ -394,9 +399,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
       if (warp == kEpiWarps) TC_STAMP(16);
       mbar_wait_backoff(&g0done, tile_no & 1);              // G0 of this tile is complete (hence every MMA of the previous tile)
       if (warp == kEpiWarps) TC_STAMP(17);
-      if (a.mode != 0 && alu) {
+      if (a.mode != 0 && (alu || kAluWarps == 0)) {
         colour_static_tile<P>(a, tile, row, inA0 + buf * kInBytes);
-        colour_static_tile<P>(a, tile, row + 64, inA0 + buf * kInBytes);
+        if (alu) colour_static_tile<P>(a, tile, row + 64, inA0 + buf * kInBytes);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive_remote(misc_ready_r);
