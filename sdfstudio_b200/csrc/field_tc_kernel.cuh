@@ -96,6 +96,16 @@ __device__ __forceinline__ void store_chunk(uint8_t* inA, int row, int chunk, co
 // accurate sin / sincos as real calls: one copy of the (long) range-reduction code instead of one per call site -- the roles of this
 // kernel share the SM's instruction cache, and `no instruction` stalls were 20 % of all samples with everything inlined
 // L2 eviction priorities (0 normal, 1 evict_first, 2 evict_last) of the hash table and of the per-CTA scratch spills (A/B measured)
+// 1: the hash gathers of the NEXT tile start only after this tile's E1 (the two softplus epilogues spill 64 + 128 KB through the same L1
+// request queue the gathers saturate; keeping them apart costs nothing because the gathers need < half of a tile's time)
+#ifndef TCV_GATHER_AFTER_E1
+#define TCV_GATHER_AFTER_E1 1
+#endif
+// pause (ns) of a gather thread after each hash level: the gathers are off the critical path, so they are spread over the tile instead
+// of saturating the L1 request queue that the epilogues' spills / reloads share
+#ifndef TCV_GATHER_NAP
+#define TCV_GATHER_NAP 600
+#endif
 #ifndef TCV_POL_TABLE
 #define TCV_POL_TABLE 2
 #endif
@@ -138,6 +148,7 @@ __device__ __forceinline__ void encode_tile_grid(const TcArgs& a, int tile, int 
       level_prepare<LAYOUT>(a.grid, l, x01, y01, z01, c);
       level_fetch_rt2(a.grid, a.table, c, tv, pol_table);
       level_finish<2, LAYOUT>(a.grid, c, tv, o, dj);
+      if (TCV_GATHER_NAP > 0 && a.mode != 0) __nanosleep(TCV_GATHER_NAP);
     }
     store_in<P>(inA, row, 2 * l, o[0]);
     store_in<P>(inA, row, 2 * l + 1, o[1]);
@@ -240,7 +251,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
   float* prm = fbuf + 6 * 128;        // [9][256] biases / fp32 weight rows used by the epilogues
   float* racc = prm + 9 * 256;        // [8][4] per-ray accumulators of the fused compositing (rays spanning several warps)
   float* lastrgb = racc + 32;         // [4][3]
-  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_ready, in_ready, misc_ready;
+  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_ready, in_ready, misc_ready, e1done;
   __shared__ double wtot[4];
   __shared__ uint32_t tmem_base_s;
 
@@ -252,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     mbar_init(&dfull, 1);
     mbar_init(&g0done, 1);
     mbar_init(&a_ready, 2 * kEpiWarps);
+    mbar_init(&e1done, kEpiWarps);
     mbar_init(&in_ready, 2 * kEncWarps);
     mbar_init(&misc_ready, 2 * (kAluWarps > 0 ? kAluWarps : kGatherWarps));
     fence_barrier_init();
@@ -407,6 +419,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         if (lane == 0) mbar_arrive_remote(misc_ready_r);
       }
       if (warp == kEpiWarps) TC_STAMP(18);
+      if (TCV_GATHER_AFTER_E1 && !alu && a.mode != 0) mbar_wait_backoff(&e1done, tile_no & 1);   // this CTA's E1 (h2 spill) is through
       if (tp + npairs < a.n_tile_pairs) encode(tile + 2 * npairs, inA0 + (buf ^ 1) * kInBytes, enc_s + (size_t)(buf ^ 1) * kJRBytes);
       if (warp == kEpiWarps) TC_STAMP(19);
     }
@@ -543,6 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
       tc_wait_st();
       red[q * 128 + row] = sdf_part;
       if (a.mode != 0) epi_arrive(); else tc_fence_before();
+      if (TCV_GATHER_AFTER_E1 && a.mode != 0 && lane == 0) mbar_arrive(&e1done);
       if (warp == 0) TC_STAMP(5);
       named_sync(2, kEpiThreads);
       const float sdf = (red[row] + red[128 + row]) + sdf_bias;
