@@ -17,7 +17,11 @@ constexpr int kEncWarps = kGatherWarps + kAluWarps;
 constexpr int kWarpProducer = kEpiWarps + kEncWarps;         // 14
 constexpr int kWarpMma = kWarpProducer + 1;                  // 15
 constexpr int kTcThreads = (kWarpMma + 1) * 32;              // 512: register allocation rounds the warp count up to a multiple of 4 anyway
-constexpr int kStages = 7;
+#ifndef TCV_STAGES
+#define TCV_STAGES 4
+#endif
+constexpr int kStages = TCV_STAGES;      // weight ring depth (16 KB per stage and CTA at two planes).  4, not 7: the 48 KB go to L1 (carve-out 228 -> 196 KB), which
+                                         // the hash gathers of the coarse levels need more than the MMA issuer needs look-ahead (A/B: 7 -> 1.59 ms, 4 -> 1.47 ms)
 constexpr int kKB = 32;           // K per streamed weight block of the 256-row layers (one 16 KB stage per CTA at two planes)
 constexpr int kKBMax = 64;        // the 96-row layer streams K blocks of 64 (12 KB): deeper prefetch in bytes for the short layers
 constexpr int kMaxGridDim = 32;

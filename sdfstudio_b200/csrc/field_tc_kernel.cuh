@@ -8,7 +8,10 @@
 // Per tile (everything stays on chip except three L2-resident spills):
 //   encode   4 gather warps (one thread per point), decoupled from the compute warps and one tile ahead: position,
 //            contraction, hash gathers (+ jacobian), PE -> bf16 split planes in smem (double buffered)
-//   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), next layer's A operand written to TMEM
+//   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), converted IN PLACE into the next layer's A operand
+//            (bf16 planes, K step j at columns 16 j (hi) / 16 j + 8 (lo) of the accumulator it came from); the two 256-column halves
+//            of TMEM (X, Y) alternate as accumulator / A operand from layer to layer, and the next layer's MMAs TRAIL the epilogue:
+//            every 64 converted columns are handed to the MMA issuer (a_rdy[0..3]), so the tensor pipe runs under the epilogue
 //   sdf      fp32 dot of h2 with row 0 of W2 on CUDA cores (exact fp32: the SDF drives NeuS alpha / Laplace density)
 //   (no G2)  the geo feature is linear in h2, so colour layer 0 is pre-multiplied at pack time: Wc = Wgf W2', and h2 itself
 //            (bf16 planes) takes the L2-resident round trip across the reverse sweep
@@ -101,10 +104,19 @@ __device__ __forceinline__ void store_chunk(uint8_t* inA, int row, int chunk, co
 #ifndef TCV_GATHER_AFTER_E1
 #define TCV_GATHER_AFTER_E1 1
 #endif
-// pause (ns) of a gather thread after each hash level: the gathers are off the critical path, so they are spread over the tile instead
-// of saturating the L1 request queue that the epilogues' spills / reloads share
+// pause (ns) of a gather thread after each hash level (spreads the gathers over the tile).  0 since the MMAs trail the epilogues: a tile is
+// short enough now that the encode of the next tile (~45 k cycles of gathers) must not be stretched (A/B: 600 -> 1.47 ms, 0 -> 1.44 ms)
 #ifndef TCV_GATHER_NAP
-#define TCV_GATHER_NAP 600
+#define TCV_GATHER_NAP 0
+#endif
+// epilogue waits for an MMA phase: 1 = plain spin on try_wait (shortest wake-up; the phases are short now that the MMAs trail the epilogues)
+#ifndef TCV_EPI_SPIN
+#define TCV_EPI_SPIN 0
+#endif
+#if TCV_EPI_SPIN
+#define EPI_WAIT(bar, par) mbar_wait(bar, par)
+#else
+#define EPI_WAIT(bar, par) mbar_wait_backoff(bar, par)
 #endif
 #ifndef TCV_POL_TABLE
 #define TCV_POL_TABLE 2
@@ -251,7 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
   float* prm = fbuf + 6 * 128;        // [9][256] biases / fp32 weight rows used by the epilogues
   float* racc = prm + 9 * 256;        // [8][4] per-ray accumulators of the fused compositing (rays spanning several warps)
   float* lastrgb = racc + 32;         // [4][3]
-  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_ready, in_ready, misc_ready, e1done;
+  __shared__ uint64_t full[kStages], empty[kStages], peer_full[kStages], dfull, g0done, a_rdy[8], x_free, c0_ready, in_ready, misc_ready, e1done;
   __shared__ double wtot[4];
   __shared__ uint32_t tmem_base_s;
 
@@ -262,7 +274,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&peer_full[s], 1); }
     mbar_init(&dfull, 1);
     mbar_init(&g0done, 1);
-    mbar_init(&a_ready, 2 * kEpiWarps);
+    for (int g = 0; g < 8; ++g) mbar_init(&a_rdy[g], 2 * kEpiWarps);
+    mbar_init(&x_free, 2 * kEpiWarps);
+    mbar_init(&c0_ready, 2 * kEpiWarps);
     mbar_init(&e1done, kEpiWarps);
     mbar_init(&in_ready, 2 * kEncWarps);
     mbar_init(&misc_ready, 2 * (kAluWarps > 0 ? kAluWarps : kGatherWarps));
@@ -284,11 +298,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
   cluster_sync_all();                      // barriers of both CTAs initialised before any remote arrive / multicast commit
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t d_tmem = tmem;          // accumulator: columns [0,256)
-  const uint32_t a_tmem = tmem + 256;    // A planes: plane p at columns 256 + 128 p
+  // two 256-column regions; per layer one is the accumulator and the other holds the A operand (the previous accumulator, converted in place):
+  //   G0: D=X | G1: A=X D=Y | B1: A=Y D=X | B0: A=X D=Y[0,96) | C0H (+C0MISC): A=X (h2 reloaded) D=Y | C1: A=Y D=X
+  const uint32_t x_tmem = tmem;
+  const uint32_t y_tmem = tmem + 256;
   const int nphase_layers = a.mode == 0 ? 2 : L_COUNT;
   // leader-side barriers that both CTAs arrive on
-  const uint32_t a_ready_r = mapa_shared(smem_u32(&a_ready), 0);
+  const uint32_t a_rdy_r0 = mapa_shared(smem_u32(&a_rdy[0]), 0);      // a_rdy[g] of the leader CTA: + 8 g
+  const uint32_t x_free_r = mapa_shared(smem_u32(&x_free), 0);
+  const uint32_t c0_ready_r = mapa_shared(smem_u32(&c0_ready), 0);
   const uint32_t in_ready_r = mapa_shared(smem_u32(&in_ready), 0);
   const uint32_t misc_ready_r = mapa_shared(smem_u32(&misc_ready), 0);
 
@@ -325,28 +343,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
       }
     } else if (lane == 0) {
       // ============================== MMA issuer (leader CTA, one thread) ==============================
-      uint32_t it = 0, par_a = 0, par_in = 0, par_misc = 0;
+      uint32_t it = 0, par_a = 0, par_in = 0, par_misc = 0, par_x = 0, par_c0 = 0;
       int tile_no = -1;
       for (int tp = pair; tp < a.n_tile_pairs; tp += npairs) {
         ++tile_no;
         const uint32_t in_base = smem_u32(inA0 + (tile_no & 1) * kInBytes);
         for (int L = 0; L < nphase_layers; ++L) {
-          if (L == L_C0MISC) {                                   // accumulates onto C0H; its static columns come from the gather warps
+          const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
+          if (L == L_C0MISC) {                                   // accumulates onto C0H; static columns from the gather warps, chunk 0 (gradient) from EB0
             mbar_wait_cluster(&misc_ready, par_misc); par_misc ^= 1;
-          } else {
-            mbar_wait_cluster(&a_ready, par_a); par_a ^= 1;     // both CTAs: A operand of this layer staged, D drained
-            if (L == L_G0) { mbar_wait_cluster(&in_ready, par_in); par_in ^= 1; }
+            mbar_wait_cluster(&c0_ready, par_c0); par_c0 ^= 1;
+          } else if (L == L_G0) {
+            mbar_wait_cluster(&x_free, par_x); par_x ^= 1;      // both CTAs: region X drained (EC1 / sdf-only E1 of the previous tile)
+            mbar_wait_cluster(&in_ready, par_in); par_in ^= 1;
           }
-          tc_fence_after();
+          if (a_in_smem) tc_fence_after();
           TC_STAMP(20 + L);
           const TcLayer ly = a.layer[L];
-          const bool a_in_smem = (L == L_G0 || L == L_C0MISC);
+          const uint32_t d_tmem = (L == L_G0 || L == L_B1 || L == L_C1) ? x_tmem : y_tmem;
+          const uint32_t a_tmem = (L == L_G1 || L == L_B0 || L == L_C0H) ? x_tmem : y_tmem;
+          const int groups_per_kb = 8 / ly.nkb;                  // TS layers: K = 256 arrives in 8 groups of 32 columns, handed over one by one by the epilogue
           const uint32_t idesc = make_idesc_bf16(256, ly.Np);
           const uint32_t lbo_b = (uint32_t)(ly.Np / 2) * 16, plane_b = (uint32_t)(ly.Np / 2) * ly.kblk * 2;
           const int ksteps = ly.kblk / 16;
           uint32_t acc = (L == L_C0MISC) ? 1u : 0u;
           for (int kb = 0; kb < ly.nkb; ++kb, ++it) {
             const int s = it % kStages;
+            if (!a_in_smem)
+              for (int g = kb * groups_per_kb; g < (kb + 1) * groups_per_kb; ++g) mbar_wait_cluster(&a_rdy[g], par_a);   // both CTAs: these A columns are in place
             mbar_wait(&full[s], (it / kStages) & 1);
             mbar_wait_cluster(&peer_full[s], (it / kStages) & 1);
             tc_fence_after();
@@ -366,16 +390,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
                   mma_ss2(d_tmem, a0, b1, idesc, 1);
                 }
               } else {
-                mma_ts2(d_tmem, a_tmem + kstep * 8, b0, idesc, acc);
+                mma_ts2(d_tmem, a_tmem + kstep * 16, b0, idesc, acc);
                 acc = 1;
                 if (P > 1) {
-                  mma_ts2(d_tmem, a_tmem + 128 + kstep * 8, b0, idesc, 1);
-                  mma_ts2(d_tmem, a_tmem + kstep * 8, b1, idesc, 1);
+                  mma_ts2(d_tmem, a_tmem + kstep * 16 + 8, b0, idesc, 1);
+                  mma_ts2(d_tmem, a_tmem + kstep * 16, b1, idesc, 1);
                 }
               }
             }
             mma_commit2(&empty[s]);
           }
+          if (!a_in_smem) par_a ^= 1;
           if (L == L_G0) mma_commit2(&g0done);               // the geo input of this tile has been consumed (gather warps)
           if (L != L_C0H) mma_commit2(&dfull);               // C0H is completed by C0MISC
         }
@@ -444,10 +469,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
     uint32_t dpar = 0;
     const uint64_t pol_stream = l2_policy(TCV_POL_SCRATCH);
     const uint64_t pol_keep = l2_policy_evict_normal();
-    auto epi_arrive = [&]() {
+    // hand 32 converted A columns (K group g = this iteration's chunk of both column-half threads) to the MMA issuer
+    auto sub_arrive = [&](int g) {
+      tc_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_remote(a_ready_r);
+      if (lane == 0) mbar_arrive_remote(a_rdy_r0 + 8 * g);
+    };
+    auto x_arrive = [&]() {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(x_free_r);
     };
 
     int tile_no = -1;
@@ -467,17 +499,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         if (a.out.points_norm) a.out.points_norm[p] = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py)), __fmul_rn(pz, pz)));
         if (a.out.points) { a.out.points[p * 3] = px; a.out.points[p * 3 + 1] = py; a.out.points[p * 3 + 2] = pz; }
       }
-      if (tile_no == 0 || a.mode == 0) epi_arrive();      // D and the A planes are free (later tiles: signalled at the end of EC1 of the previous tile)
+      if (tile_no == 0 || a.mode == 0) x_arrive();        // region X is free (later tiles: signalled at the end of EC1 of the previous tile)
       if (warp == 0) TC_STAMP(1);
 
       // ---------------- E0: h1 = softplus(z1) -> A planes ; softplus'(z1) -> scratch ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
       if (warp == 0) TC_STAMP(2);
+      // thread (row, q) converts the 16-column chunks 2 i + q, i = 0..7: after every iteration 32 more columns (one K group) are done
 #pragma unroll 1
       for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
+        const int col0 = (2 * cc + q) * 16;
         uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
+        tmem_ld16(x_tmem + lane_addr + col0, v);
         tc_wait_ld();
         uint32_t hi[8], lo[8];
         float sg[16];
@@ -492,8 +525,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
           split2(h0, h1, hi[j >> 1], lo[j >> 1]);
           split2(h2, h3, hi[(j >> 1) + 1], lo[(j >> 1) + 1]);
         }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
+        tmem_st8(x_tmem + lane_addr + col0, hi);
+        if (P > 1) tmem_st8(x_tmem + lane_addr + col0 + 8, lo);
+        sub_arrive(cc);
         if (a.mode != 0) {
 #pragma unroll
           for (int u8 = 0; u8 < 2; ++u8) {
@@ -508,20 +542,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
           }
         }
       }
-      tc_wait_st();
-      epi_arrive();
       if (warp == 0) TC_STAMP(3);
 
       // ---------------- E1: h2 -> scratch planes (colour layer 0 input) ; sdf = W2[0,:] . h2 + b (fp32) ;
       //                      g2 = W2[0,:] * softplus'(z2) -> A planes (seed of the reverse sweep)
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
       if (warp == 0) TC_STAMP(4);
       float sdf_part = 0.f;
 #pragma unroll 1
       for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
+        const int col0 = (2 * cc + q) * 16;
         uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
+        tmem_ld16(y_tmem + lane_addr + col0, v);
         tc_wait_ld();
         uint32_t hi[8], lo[8], ghi[8], glo[8];
 #pragma unroll
@@ -549,13 +581,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
             st_stream(gf_s + unit, make_uint4(hi[4 * u8], hi[4 * u8 + 1], hi[4 * u8 + 2], hi[4 * u8 + 3]), pol_stream);
             if (P > 1) st_stream(gf_s + 65536 + unit, make_uint4(lo[4 * u8], lo[4 * u8 + 1], lo[4 * u8 + 2], lo[4 * u8 + 3]), pol_stream);
           }
-          tmem_st8(a_tmem + lane_addr + (col0 >> 1), ghi);
-          if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), glo);
+          tmem_st8(y_tmem + lane_addr + col0, ghi);
+          if (P > 1) tmem_st8(y_tmem + lane_addr + col0 + 8, glo);
+          sub_arrive(cc);
         }
       }
-      tc_wait_st();
       red[q * 128 + row] = sdf_part;
-      if (a.mode != 0) epi_arrive(); else tc_fence_before();
+      if (a.mode == 0) tc_fence_before();
       if (TCV_GATHER_AFTER_E1 && a.mode != 0 && lane == 0) mbar_arrive(&e1done);
       if (warp == 0) TC_STAMP(5);
       named_sync(2, kEpiThreads);
@@ -571,14 +603,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
       {
         uint4 sp[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) sp[u] = ld_stream_u4(sig_s + ((size_t)(q * 16 + u) * 128 + row) * 16, pol_stream);
-        mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+        for (int u = 0; u < 16; ++u) sp[u] = ld_stream_u4(sig_s + ((size_t)((2 * (u >> 1) + q) * 2 + (u & 1)) * 128 + row) * 16, pol_stream);   // units of chunk 2 i + q
+        EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
         TC_STAMP(8);
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
-          const int col0 = q * 128 + cc * 16;
+          const int col0 = (2 * cc + q) * 16;
           uint32_t v[16];
-          tmem_ld16(d_tmem + lane_addr + col0, v);
+          tmem_ld16(x_tmem + lane_addr + col0, v);
           tc_wait_ld();
           uint32_t hi[8], lo[8];
           const uint32_t spw[8] = {sp[2 * cc].x, sp[2 * cc].y, sp[2 * cc].z, sp[2 * cc].w, sp[2 * cc + 1].x, sp[2 * cc + 1].y, sp[2 * cc + 1].z, sp[2 * cc + 1].w};
@@ -587,12 +619,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
             const float s0 = (float)(spw[j] & 0xFFFFu) * (1.0f / 65535.0f), s1 = (float)(spw[j] >> 16) * (1.0f / 65535.0f);
             split2(__uint_as_float(v[2 * j]) * s0, __uint_as_float(v[2 * j + 1]) * s1, hi[j], lo[j]);
           }
-          tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-          if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
+          tmem_st8(x_tmem + lane_addr + col0, hi);
+          if (P > 1) tmem_st8(x_tmem + lane_addr + col0 + 8, lo);
+          sub_arrive(cc);
         }
       }
-      tc_wait_st();
-      epi_arrive();
       TC_STAMP(9);
 
       // ---------------- EB0: gin (96 cols, kernel order) . input jacobian -> d sdf / dx ; gradient chunk of the colour operand ;
@@ -621,12 +652,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
           const int xj = i - a.pe_dim;
           jp[j] = is_pe ? ld_stream_f1(Jpe + i * 128 + row, pol_keep) : ((xj >= 0 && xj < 3 && (j < 16 || q == 0)) ? 1.f : 0.f);
         }
-        mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+        EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
         TC_STAMP(10);
         uint32_t gin_v[8];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          tmem_ld8(d_tmem + lane_addr + (2 * q + c) * 8, gin_v);
+          tmem_ld8(y_tmem + lane_addr + (2 * q + c) * 8, gin_v);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -638,7 +669,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         for (int c = 0; c < 3; ++c) {
           if (c < 2 || q == 0) {
             const int ck = c < 2 ? 4 + 2 * q + c : 8;
-            tmem_ld8(d_tmem + lane_addr + ck * 8, gin_v);
+            tmem_ld8(y_tmem + lane_addr + ck * 8, gin_v);
             tc_wait_ld();
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -653,25 +684,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         }
       }
       red[(0 * 2 + q) * 128 + row] = gx; red[(1 * 2 + q) * 128 + row] = gy; red[(2 * 2 + q) * 128 + row] = gz;
-      // h2 planes back into the A operand for colour layer 0 (two batches of 8 units: all L2 loads of a batch in flight together)
+      // h2 planes back into region X as the A operand of colour layer 0 (B0, whose A operand X held, is complete; the gin columns of Y
+      // have been read above, so C0H may overwrite Y).  Two batches of 8 units (all L2 loads of a batch in flight together); a batch covers
+      // the K groups 2 hb, 2 hb + 1: thread (row, q) brings the units 8 g + 4 q .. + 3 of each group g.
 #pragma unroll 1
       for (int hb = 0; hb < 2; ++hb) {
         uint4 gh[8], gl[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-          const size_t unit = ((size_t)(q * 16 + hb * 8 + u) * 128 + row) * 16;
+          const int un = 8 * (2 * hb + (u >> 2)) + 4 * q + (u & 3);
+          const size_t unit = ((size_t)un * 128 + row) * 16;
           gh[u] = ld_stream_u4(gf_s + unit, pol_stream);
           if (P > 1) gl[u] = ld_stream_u4(gf_s + 65536 + unit, pol_stream);
         }
 #pragma unroll
         for (int u = 0; u < 8; u += 2) {
+          const int un = 8 * (2 * hb + (u >> 2)) + 4 * q + (u & 3);      // even: K step un / 2 at columns 16 (un / 2)
           const uint32_t h8[8] = {gh[u].x, gh[u].y, gh[u].z, gh[u].w, gh[u + 1].x, gh[u + 1].y, gh[u + 1].z, gh[u + 1].w};
-          tmem_st8(a_tmem + lane_addr + (q * 16 + hb * 8 + u) * 4, h8);
+          tmem_st8(x_tmem + lane_addr + (un >> 1) * 16, h8);
           if (P > 1) {
             const uint32_t l8[8] = {gl[u].x, gl[u].y, gl[u].z, gl[u].w, gl[u + 1].x, gl[u + 1].y, gl[u + 1].z, gl[u + 1].w};
-            tmem_st8(a_tmem + 128 + lane_addr + (q * 16 + hb * 8 + u) * 4, l8);
+            tmem_st8(x_tmem + lane_addr + (un >> 1) * 16 + 8, l8);
           }
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) sub_arrive(4 * hb + g);
       }
       named_sync(2, kEpiThreads);
       const float grx = red[(0 * 2 + 0) * 128 + row] + red[(0 * 2 + 1) * 128 + row];
@@ -684,19 +721,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         const float c0v[8] = {grx, gry, grz, a.use_n_dot_v ? nx * dirx + ny * diry + nz * dirz : 0.f, 0.f, 0.f, 0.f, 0.f};
         store_chunk<P>(inA, row, 0, c0v);
       }
-      tc_wait_st();
+      // chunk 0 of the colour operand (gradient, n.v) is in shared memory: C0MISC may run
       fence_async_smem();
-      epi_arrive();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(c0_ready_r);
       if (warp == 0) TC_STAMP(11);
 
       // ---------------- EC0: relu -> A planes ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
       if (warp == 0) TC_STAMP(12);
 #pragma unroll 1
       for (int cc = 0; cc < 8; ++cc) {
-        const int col0 = q * 128 + cc * 16;
+        const int col0 = (2 * cc + q) * 16;
         uint32_t v[16];
-        tmem_ld16(d_tmem + lane_addr + col0, v);
+        tmem_ld16(y_tmem + lane_addr + col0, v);
         tc_wait_ld();
         uint32_t hi[8], lo[8];
 #pragma unroll
@@ -704,15 +742,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
           const float2 b2 = *reinterpret_cast<const float2*>(p_bc0 + col0 + j);
           split2(fmaxf(__uint_as_float(v[j]) + b2.x, 0.f), fmaxf(__uint_as_float(v[j + 1]) + b2.y, 0.f), hi[j >> 1], lo[j >> 1]);
         }
-        tmem_st8(a_tmem + lane_addr + (col0 >> 1), hi);
-        if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + (col0 >> 1), lo);
+        tmem_st8(y_tmem + lane_addr + col0, hi);
+        if (P > 1) tmem_st8(y_tmem + lane_addr + col0 + 8, lo);
+        sub_arrive(cc);
       }
-      tc_wait_st();
-      epi_arrive();
       if (warp == 0) TC_STAMP(13);
 
       // ---------------- EC1: relu, last colour layer (256 -> 3) as fp32 dots ----------------
-      mbar_wait_backoff(&dfull, dpar); dpar ^= 1; tc_fence_after();
+      EPI_WAIT(&dfull, dpar); dpar ^= 1; tc_fence_after();
       if (warp == 0) TC_STAMP(14);
       {
         float r0 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -720,7 +757,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         for (int cc = 0; cc < 8; ++cc) {
           const int col0 = q * 128 + cc * 16;
           uint32_t v[16];
-          tmem_ld16(d_tmem + lane_addr + col0, v);
+          tmem_ld16(x_tmem + lane_addr + col0, v);
           tc_wait_ld();
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
@@ -740,7 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1) k_fie
         red[(0 * 2 + q) * 128 + row] = r0; red[(1 * 2 + q) * 128 + row] = r1; red[(2 * 2 + q) * 128 + row] = r2;
       }
       // the accumulator and the A planes are drained: the next tile's G0 may start while the heads / compositing of this tile run
-      if (tp + npairs < a.n_tile_pairs) epi_arrive(); else tc_fence_before();
+      if (tp + npairs < a.n_tile_pairs) x_arrive(); else tc_fence_before();
       named_sync(2, kEpiThreads);
       if (q == 0) {
         // ---------------- per-point heads ----------------
