@@ -15,6 +15,8 @@ Workloads (BASELINE.json configs; the default is the headline the metric is quot
   angelo-train-8192           configs[3]: neus-facto-angelo training step (numerical gradients, hash F=8) at 8192 rays per GPU with the
                               gradient all-reduce over NCCL inside the timed region.
 
+training_step (headline line only): the angelo-train-8192 step measured at the same N in child processes (one per rank, own NCCL
+          rendezvous): train rays/s with the DistributedDataParallel gradient all-reduce inside the timed region, `allreduce_alone_ms`.
 value   : whole-job rays/s, inputs resident in HBM, CUDA-event time (max over ranks), L2 flushed between steps.
 e2e     : same metric through the public module API with HOST (pinned) ray buffers: H2D of the rays and D2H of the rendered
           rgb / depth / normal / accumulation inside the timed region (the headline workload replays one CUDA graph per step).
@@ -257,6 +259,35 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def train_section(world, rank, steps=5, warmup=3, timeout=300):
+    """BASELINE.json configs[3] next to the headline: every rank runs tools/train_workload.py (8192 rays per GPU, DistributedDataParallel gradient
+    all-reduce over NCCL inside the timed region) in a child process on its own GPU with its own rendezvous (MASTER_PORT + 17), so that the
+    driver's 1/2/4/8-GPU runs of this file also measure the one collective of the path.  Isolated on purpose: a failure or a hang of the
+    training step cannot take the headline measurement down (the child is killed after `timeout` seconds and the section reports the error)."""
+    import subprocess
+
+    env = dict(os.environ)
+    env.pop("TORCHELASTIC_USE_AGENT_STORE", None)          # the child's rank 0 hosts its own store
+    env.pop("TORCHELASTIC_RUN_ID", None)
+    if world > 1:
+        env["MASTER_PORT"] = str(int(env.get("MASTER_PORT", "29500")) + 17)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "train_workload.py"), "--steps", str(steps), "--warmup", str(warmup)]
+    try:
+        p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout)
+    except subprocess.TimeoutExpired:
+        return {"workload": "angelo-train-8192", "error": f"timed out after {timeout} s"}
+    if rank != 0:
+        return None
+    lines = [l for l in p.stdout.splitlines() if l.startswith("{")]
+    if p.returncode != 0 or not lines:
+        return {"workload": "angelo-train-8192", "error": (p.stderr or p.stdout).strip().splitlines()[-1][:300] if (p.stderr or p.stdout).strip() else f"exit code {p.returncode}"}
+    t = json.loads(lines[-1])
+    return {"workload": "angelo-train-8192", "metric": t["metric"], "value": t["value"], "unit": t["unit"], "n_gpus": t["n_gpus"], "steps": t["steps"], "warmup": t["warmup"],
+            "ms_per_step": t["ms_per_step"], "scaling": "weak", "rays_per_gpu": t["config"]["rays_per_gpu"], "parallelism": t["config"]["parallelism"],
+            "gradient_bytes": t["config"]["gradient_bytes"], "allreduce_alone_ms": t["config"]["allreduce_alone_ms"], "e2e": t["e2e"], "gpu_launches": t["gpu_launches"],
+            "roofline": t["roofline"], "loss": t["loss"]}
+
+
 # ------------------------------------------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -269,6 +300,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--unfused", action="store_true", help="A/B: separate field and compositing launches (per-sample heads through HBM)")
     ap.add_argument("--no-graph", action="store_true", help="A/B: e2e without CUDA-graph replay")
+    ap.add_argument("--no-train-section", action="store_true", help="skip the training-step section (angelo-train-8192 with the NCCL gradient all-reduce) of the headline line")
     ap.add_argument("--table-dtype", default="fp32", choices=["fp32", "fp16"], help="fp16 = gather from a half-precision copy (tiny-cuda-nn's storage)")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -496,6 +528,12 @@ def main():
         e2e_ms = sum(a.elapsed_time(b) for a, b in pairs2)
         clk = clocks.stop() if rank == 0 else None
 
+    # ---- the training step of the path (configs[3]) with its gradient all-reduce, measured next to the headline at the same N ----
+    train = None
+    if wl == WORKLOAD and not args.no_train_section:
+        torch.cuda.empty_cache()
+        train = train_section(world, rank)
+        barrier()
     times = torch.tensor([dev_ms, e2e_ms, fld_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -526,6 +564,8 @@ def main():
             "cpu_baseline": cpu, "clocks": clk,
         }  # fmt: skip
         line.update(extra)
+        if train is not None:
+            line["training_step"] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -194,3 +194,14 @@ def main(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    # stand-alone entry (bench.py's headline workload spawns it once per rank to attach the training step to its line)
+    import argparse
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--precision", default="auto")
+    main(ap.parse_args())
