@@ -87,6 +87,16 @@ int sdfb200_grid_encode_backward(const sdfb200_grid_t* grid, const void* table, 
 int sdfb200_grid_encode_backward_backward(const sdfb200_grid_t* grid, const void* table, const float* x01, const float* dout,
                                           const float* g_dx01, int64_t n, float* g_dout, float* g_table, float* g_x01, void* stream);
 
+/* Grouped forms of the two calls above for numerical-gradient fields (SDFField.gradient with use_numerical_gradients,
+ * sdf_field.py:424-452: the network is evaluated at x and at x +- delta e_i).  The batch holds `group` taps per sample, tap gi of
+ * sample s at row gi * (n / group) + s; taps that hit the same 8 table rows of a level share one set of gathers / one set of atomic
+ * adds.  Results equal the ungrouped calls on the same n points (forward: bit for bit; backward: up to the order of the atomic sums).
+ * The backward produces the table gradient only (numerical-gradient fields never differentiate the encoding w.r.t. its input). */
+int sdfb200_grid_encode_grouped(const sdfb200_grid_t* grid, const void* table, const float* x01, int64_t n, int32_t group, float* out,
+                                int64_t out_ld, void* stream);
+int sdfb200_grid_encode_backward_grouped(const sdfb200_grid_t* grid, const float* x01, const float* dout, int64_t n, int32_t group,
+                                         float* dtable, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * SDFField.  Replaces nerfstudio/fields/sdf_field.py: forward_geonetwork :380-410, gradient :424-465, get_alpha
  * :476-525, get_colors :532-612, get_outputs :614-689, LaplaceDensity :57-66, get_occupancy :527-530,

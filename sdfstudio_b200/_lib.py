@@ -85,6 +85,8 @@ _PROTOS = {
     "sdfb200_struct_size": (_sz, [_i32]),
     "sdfb200_grid_encode": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _i64, _vp, _i64, _vp, _vp]),
     "sdfb200_grid_encode_backward": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _vp, _i64, _vp, _vp, _vp]),
+    "sdfb200_grid_encode_grouped": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _i64, _i32, _vp, _i64, _vp]),
+    "sdfb200_grid_encode_backward_grouped": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _i64, _i32, _vp, _vp]),
     "sdfb200_grid_encode_backward_backward": (C.c_int, [C.POINTER(GridDesc), _vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp]),
     "sdfb200_render_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sdfb200_weights_backward": (C.c_int, [_vp, _vp, _i32, _i64, _i32, _vp, _vp, _i32, _vp, _vp]),

@@ -126,6 +126,115 @@ __global__ void __launch_bounds__(256) k_grid_encode_bwd(const __grid_constant__
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Grouped variants for numerical-gradient fields (sdf_field.py:424-452): the batch holds `group` points per sample -- the sample and
+// its +-delta taps, point gi of sample n at row gi * n_samples + n -- that almost always fall into the SAME cell of a level (delta is the
+// finest level's cell size, the active levels are coarser).  One thread walks the taps of a (sample, level): while the 8 table rows
+// stay the same it gathers them once (forward) / accumulates the 8 row gradients in registers and issues ONE set of atomics
+// (backward) instead of `group` of them.  Arithmetic per point is the ungrouped kernels' (same prepare / finish expression trees).
+// -----------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool same_rows(const LevelCtx& a, const LevelCtx& b) {
+  bool same = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) same = same && (a.idx[k] == b.idx[k]);
+  return same;
+}
+
+template <typename T, int F>
+__global__ void __launch_bounds__(256) k_grid_encode_grouped(const __grid_constant__ sdfb200_grid_t g, const void* __restrict__ table,
+                                                             const float* __restrict__ x01, int64_t n_samples, int group, float* __restrict__ out,
+                                                             int64_t out_ld) {
+  const int L = g.n_levels;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_samples * L) return;
+  const int64_t n = idx / L;
+  const int l = (int)(idx - n * L);
+  LevelCtx cur;
+  float tv[8][F];
+  bool have = false;
+  for (int gi = 0; gi < group; ++gi) {
+    const int64_t p = (int64_t)gi * n_samples + n;
+    float o[F];
+    if (l < g.active_levels) {
+      LevelCtx c;
+      level_prepare(g, l, __ldg(x01 + p * 3), __ldg(x01 + p * 3 + 1), __ldg(x01 + p * 3 + 2), c);
+      if (!have || !same_rows(c, cur)) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) TableLoad<T, F>::load(table, c.base + c.idx[k], tv[k]);
+        have = true;
+      }
+      cur = c;
+      float dj[F][3];
+      level_finish<F>(g, c, tv, o, dj);
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) o[f] = 0.f;
+    }
+    float* op = out + p * out_ld + l * F;
+#pragma unroll
+    for (int f = 0; f < F; ++f) op[f] = o[f];
+  }
+}
+
+// weight of table row k (LevelCtx order) in the blend of level_finish
+__device__ __forceinline__ void corner_weights(const sdfb200_grid_t& g, const LevelCtx& c, float (&w)[8]) {
+  if (g.layout == SDFB200_GRID_TORCH) {
+    const float ox = c.w[0], oy = c.w[1], oz = c.w[2], nx = 1.f - ox, ny = 1.f - oy, nz = 1.f - oz;
+    // (c,c,c)(c,f,c)(f,f,c)(f,c,c)(c,c,f)(c,f,f)(f,f,f)(f,c,f): the CEIL corner carries the offset
+    w[0] = ox * oy * oz; w[1] = ox * ny * oz; w[2] = nx * ny * oz; w[3] = nx * oy * oz;
+    w[4] = ox * oy * nz; w[5] = ox * ny * nz; w[6] = nx * ny * nz; w[7] = nx * oy * nz;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      w[k] = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(256) k_grid_encode_bwd_grouped(const __grid_constant__ sdfb200_grid_t g, const float* __restrict__ x01,
+                                                                 const float* __restrict__ dout, int64_t n_samples, int group,
+                                                                 float* __restrict__ dtable) {
+  const int L = g.n_levels;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_samples * L) return;
+  const int64_t n = idx / L;
+  const int l = (int)(idx - n * L);
+  if (l >= g.active_levels) return;
+  LevelCtx cur;
+  float acc[8][F];
+  bool have = false;
+  auto flush = [&]() {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) atomic_add_row<F>(dtable + (cur.base + cur.idx[k]) * F, acc[k]);
+  };
+  for (int gi = 0; gi < group; ++gi) {
+    const int64_t p = (int64_t)gi * n_samples + n;
+    LevelCtx c;
+    level_prepare(g, l, __ldg(x01 + p * 3), __ldg(x01 + p * 3 + 1), __ldg(x01 + p * 3 + 2), c);
+    if (have && !same_rows(c, cur)) {
+      flush();
+      have = false;
+    }
+    if (!have) {
+      cur = c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int f = 0; f < F; ++f) acc[k][f] = 0.f;
+      have = true;
+    }
+    float w[8], go[F];
+    corner_weights(g, c, w);
+#pragma unroll
+    for (int f = 0; f < F; ++f) go[f] = __ldg(dout + p * L * F + l * F + f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int f = 0; f < F; ++f) acc[k][f] = fmaf(w[k], go[f], acc[k][f]);
+  }
+  if (have) flush();
+}
+
 // second-order backward (the backward of k_grid_encode_bwd's dx01 output), needed by the eikonal loss
 // (models/base_surface_model.py:358-362 differentiates |grad sdf| w.r.t. the parameters):
 //   first backward:  dx[c] = sum_lf dout[lf] * J[lf][c](x, table)
@@ -244,6 +353,24 @@ static int launch_encode_bwd2(const sdfb200_grid_t& g, const void* table, const 
   return 0;
 }
 
+template <typename T, int F>
+static int launch_encode_grouped(const sdfb200_grid_t& g, const void* table, const float* x01, int64_t n_samples, int group, float* out, int64_t out_ld,
+                                 cudaStream_t st) {
+  const int64_t total = n_samples * g.n_levels;
+  k_grid_encode_grouped<T, F><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(g, table, x01, n_samples, group, out, out_ld);
+  SDFB_LAUNCHED("k_grid_encode_grouped");
+  return 0;
+}
+
+template <typename T, int F>
+static int launch_encode_bwd_grouped(const sdfb200_grid_t& g, const float* x01, const float* dout, int64_t n_samples, int group, float* dtable,
+                                     cudaStream_t st) {
+  const int64_t total = n_samples * g.n_levels;
+  k_grid_encode_bwd_grouped<F><<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(g, x01, dout, n_samples, group, dtable);
+  SDFB_LAUNCHED("k_grid_encode_bwd_grouped");
+  return 0;
+}
+
 #define SDFB_DISPATCH_GRID(g, FN, ...)                                                      \
   do {                                                                                      \
     const bool h__ = (g).table_dtype == SDFB200_DT_F16;                                     \
@@ -294,4 +421,25 @@ extern "C" int sdfb200_grid_encode_backward_backward(const sdfb200_grid_t* grid,
   if (n == 0) return 0;
   SDFB_REQUIRE(table && x01 && dout && g_dx01, "NULL pointer");
   SDFB_DISPATCH_GRID(*grid, launch_encode_bwd2, *grid, table, x01, dout, g_dx01, n, g_dout, g_table, g_x01, (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_grid_encode_grouped(const sdfb200_grid_t* grid, const void* table, const float* x01, int64_t n, int32_t group, float* out,
+                                           int64_t out_ld, void* stream) {
+  int r = validate_grid(grid);
+  if (r) return r;
+  SDFB_REQUIRE(n >= 0 && group >= 1 && n % group == 0, "n must be a non-negative multiple of group");
+  if (n == 0) return 0;
+  SDFB_REQUIRE(table && x01 && out, "NULL pointer");
+  SDFB_REQUIRE(out_ld >= (int64_t)grid->n_levels * grid->n_features, "out_ld too small");
+  SDFB_DISPATCH_GRID(*grid, launch_encode_grouped, *grid, table, x01, n / group, group, out, out_ld, (cudaStream_t)stream);
+}
+
+extern "C" int sdfb200_grid_encode_backward_grouped(const sdfb200_grid_t* grid, const float* x01, const float* dout, int64_t n, int32_t group,
+                                                    float* dtable, void* stream) {
+  int r = validate_grid(grid);
+  if (r) return r;
+  SDFB_REQUIRE(n >= 0 && group >= 1 && n % group == 0, "n must be a non-negative multiple of group");
+  if (n == 0) return 0;
+  SDFB_REQUIRE(x01 && dout && dtable, "NULL pointer");
+  SDFB_DISPATCH_GRID(*grid, launch_encode_bwd_grouped, *grid, x01, dout, n / group, group, dtable, (cudaStream_t)stream);
 }

@@ -86,10 +86,17 @@ class _GridEncodeFn(torch.autograd.Function):
         x = _lib.f32c(x)
         n = x.shape[0]
         out = torch.empty(n, enc.n_output_dims, device=x.device, dtype=torch.float32)
-        _lib.check(lib.sdfb200_grid_encode(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), n, _lib.ptr(out), enc.n_output_dims, None,
-                                           _lib.stream_ptr()), "sdfb200_grid_encode")
+        # Encoding.point_groups(G): the batch is G taps per sample (tap g of sample s at row g * n / G + s) that mostly share their table rows
+        groups = enc._groups if enc._groups > 1 and n % enc._groups == 0 else 1
+        if groups > 1:
+            _lib.check(lib.sdfb200_grid_encode_grouped(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), n, groups, _lib.ptr(out), enc.n_output_dims,
+                                                       _lib.stream_ptr()), "sdfb200_grid_encode_grouped")
+        else:
+            _lib.check(lib.sdfb200_grid_encode(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), n, _lib.ptr(out), enc.n_output_dims, None,
+                                               _lib.stream_ptr()), "sdfb200_grid_encode")
         ctx.save_for_backward(x, table)
         ctx.enc = enc
+        ctx.groups = groups
         return out
 
     @staticmethod
@@ -98,7 +105,7 @@ class _GridEncodeFn(torch.autograd.Function):
         # inside Encoding.inputs_only_backward() (the autograd.grad(sdf, x) of SDFField) the table gradient is not requested:
         # skip its atomic scatter -- autograd cannot tell a Python Function which of its input gradients a call needs
         need_dtable = ctx.needs_input_grad[1] and not ctx.enc._inputs_only
-        dx, dtable = _GridEncodeBwdFn.apply(dout, x, table, ctx.enc, ctx.needs_input_grad[0], need_dtable)
+        dx, dtable = _GridEncodeBwdFn.apply(dout, x, table, ctx.enc, ctx.needs_input_grad[0], need_dtable, ctx.groups)
         return dx, dtable, None
 
 
@@ -106,7 +113,7 @@ class _GridEncodeBwdFn(torch.autograd.Function):
     """(dx, dtable) = encode_backward(dout; x, table); its own backward is sdfb200_grid_encode_backward_backward."""
 
     @staticmethod
-    def forward(ctx, dout, x, table, enc, need_dx, need_dtable):
+    def forward(ctx, dout, x, table, enc, need_dx, need_dtable, groups=1):
         lib = _lib.load()
         dout = _lib.f32c(dout)
         n = x.shape[0]
@@ -116,8 +123,13 @@ class _GridEncodeBwdFn(torch.autograd.Function):
             ctx.save_for_backward(dout, x, table)
             ctx.enc = enc
             return None, None
-        _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
-                                                    _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
+        if groups > 1 and dx is None:
+            # table gradient of a grouped batch: taps that hit the same 8 rows of a level are summed in registers, one set of atomics per run
+            _lib.check(lib.sdfb200_grid_encode_backward_grouped(enc._desc_ref(), _lib.ptr(x), _lib.ptr(dout), n, groups, _lib.ptr(dtable), _lib.stream_ptr()),
+                       "sdfb200_grid_encode_backward_grouped")
+        else:
+            _lib.check(lib.sdfb200_grid_encode_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), n, _lib.ptr(dtable),
+                                                        _lib.ptr(dx), _lib.stream_ptr()), "sdfb200_grid_encode_backward")
         ctx.save_for_backward(dout, x, table)
         ctx.enc = enc
         dt = dtable.to(table.dtype) if dtable is not None else None
@@ -129,7 +141,7 @@ class _GridEncodeBwdFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_dx, g_dtable):
         if g_dx is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         lib = _lib.load()
         dout, x, table = ctx.saved_tensors
         enc = ctx.enc
@@ -141,7 +153,7 @@ class _GridEncodeBwdFn(torch.autograd.Function):
         _lib.check(lib.sdfb200_grid_encode_backward_backward(enc._desc_ref(), _lib.ptr(enc.compute_table()), _lib.ptr(x), _lib.ptr(dout), _lib.ptr(g_dx), n,
                                                              _lib.ptr(g_dout), _lib.ptr(g_table), _lib.ptr(g_x), _lib.stream_ptr()),
                    "sdfb200_grid_encode_backward_backward")
-        return g_dout, g_x, (g_table.to(table.dtype) if g_table is not None else None), None, None, None
+        return g_dout, g_x, (g_table.to(table.dtype) if g_table is not None else None), None, None, None, None
 
 
 class Encoding(nn.Module):
@@ -156,6 +168,7 @@ class Encoding(nn.Module):
         # itself does (fp16 compute params + fp32 master); the copy is refreshed whenever the parameter changes
         self.table_dtype = table_dtype
         self._inputs_only = False
+        self._groups = 1
         self._half_cache = None
         self._half_key = None
         if n_input_dims != 3:
@@ -219,6 +232,16 @@ class Encoding(nn.Module):
             yield
         finally:
             self._inputs_only = prev
+
+    @contextlib.contextmanager
+    def point_groups(self, groups: int):
+        """Calls inside this context pass batches of `groups` taps per sample (tap g of sample s at row g * n / groups + s), e.g. a sample and its
+        six +-delta taps of the numerical gradient (sdf_field.py:424-452).  Taps that hit the same table rows share their gathers / atomics."""
+        prev, self._groups = self._groups, max(1, int(groups))
+        try:
+            yield
+        finally:
+            self._groups = prev
 
     def set_active_levels(self, levels: int):
         """levels >= `levels` output zeros (fused form of SDFField.update_mask, sdf_field.py:376-378)."""

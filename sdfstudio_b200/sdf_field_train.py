@@ -1,11 +1,12 @@
 """Differentiable (training) path of SDFField.
 
 What trains in the reference is ATen autograd over ``nn.Linear`` layers plus the ``tinycudann.Encoding`` operator
-(nerfstudio/fields/sdf_field.py:380-410, :614-689).  This module is that composition with the grid operator replaced by this
-package's kernels -- forward, backward and the second-order backward the eikonal term needs
-(sdfb200_grid_encode / _backward / _backward_backward) -- and the dense layers left to ATen exactly like the reference.
-The fused tcgen05 kernel (csrc/field_tc.cu) is the rendering / sampling path (everything under ``torch.no_grad``: the NeuS /
-error-bounded / UniSurf samplers, evaluation, mesh extraction); a fused training kernel is future work.
+(nerfstudio/fields/sdf_field.py:380-410, :614-689).  This module is that composition over this package's kernels: the grid operator
+(forward, backward, second-order backward for the eikonal term: sdfb200_grid_encode / _backward / _backward_backward, and their grouped
+forms for the seven taps of a numerical-gradient sample) and, at precision bf16x3 / bf16, the dense layers on the tcgen05 GEMMs of
+linear_ops.py (closed under differentiation); precision "fp32" keeps ATen matmuls, the reference's exact arithmetic.
+The fused tcgen05 kernel (csrc/field_tc_kernel.cuh) is the rendering / sampling path (everything under ``torch.no_grad``: the NeuS /
+error-bounded / UniSurf samplers, evaluation, mesh extraction).
 
 Functions take the SDFField module as first argument; SDFField dispatches here when autograd is recording in training mode.
 """
@@ -100,7 +101,8 @@ def gradient(field, x, skip_spatial_distortion=False, return_sdf=False):
         delta = field.numerical_gradients_delta
         offs = torch.tensor([[delta, 0, 0], [-delta, 0, 0], [0, delta, 0], [0, -delta, 0], [0, 0, delta], [0, 0, -delta]], device=x.device, dtype=x.dtype)
         points = x[None] + offs.view(6, *([1] * (x.dim() - 1)), 3)
-        points_sdf = forward_geonetwork(field, points.view(-1, 3))[..., 0].view(6, *x.shape[:-1])
+        with field.encoding.point_groups(6):               # the six taps of a sample share their table rows at all but the finest levels
+            points_sdf = forward_geonetwork(field, points.view(-1, 3))[..., 0].view(6, *x.shape[:-1])
         gradients = torch.stack([0.5 * (points_sdf[0] - points_sdf[1]) / delta, 0.5 * (points_sdf[2] - points_sdf[3]) / delta,
                                  0.5 * (points_sdf[4] - points_sdf[5]) / delta], dim=-1)
     else:
@@ -174,15 +176,27 @@ def get_outputs(field, ray_samples, return_alphas=False, return_occupancy=False)
     if field.spatial_distortion is not None:
         inputs = field.spatial_distortion(inputs)
     points_norm = inputs.norm(dim=-1)
-    if not inputs.requires_grad:
-        inputs.requires_grad_(True)
-    with torch.enable_grad():
-        h = forward_geonetwork(field, inputs)
-        sdf, geo_feature = torch.split(h, [1, c.geo_feat_dim], dim=-1)
     if c.use_numerical_gradients:
-        gradients, sampled_sdf = gradient(field, inputs, skip_spatial_distortion=True, return_sdf=True)
-        sampled_sdf = sampled_sdf.view(-1, *shape).permute(1, 2, 0).contiguous()
+        # sdf_field.py:640-645 evaluates the geo network at x and (inside gradient()) at x +- delta e_i: row-wise independent, so the seven
+        # evaluations run as ONE batch [7, N] here -- same values, and the grid operator merges the taps of a sample (Encoding.point_groups).
+        # The positions need no gradient in this mode (the reference sets requires_grad and never uses it).
+        delta = field.numerical_gradients_delta
+        offs = torch.tensor([[0, 0, 0], [delta, 0, 0], [-delta, 0, 0], [0, delta, 0], [0, -delta, 0], [0, 0, delta], [0, 0, -delta]], device=inputs.device,
+                            dtype=inputs.dtype)
+        n = inputs.shape[0]
+        with torch.enable_grad(), field.encoding.point_groups(7):
+            h_all = forward_geonetwork(field, (inputs[None] + offs[:, None, :]).view(-1, 3))
+        h = h_all[:n]
+        sdf, geo_feature = torch.split(h, [1, c.geo_feat_dim], dim=-1)
+        ps = h_all[n:, 0].view(6, n)
+        gradients = torch.stack([0.5 * (ps[0] - ps[1]) / delta, 0.5 * (ps[2] - ps[3]) / delta, 0.5 * (ps[4] - ps[5]) / delta], dim=-1)
+        sampled_sdf = ps.view(-1, *shape).permute(1, 2, 0).contiguous()
     else:
+        if not inputs.requires_grad:
+            inputs.requires_grad_(True)
+        with torch.enable_grad():
+            h = forward_geonetwork(field, inputs)
+            sdf, geo_feature = torch.split(h, [1, c.geo_feat_dim], dim=-1)
         with field.encoding.inputs_only_backward():
             gradients = torch.autograd.grad(outputs=sdf, inputs=inputs, grad_outputs=torch.ones_like(sdf), create_graph=True, retain_graph=True,
                                             only_inputs=True)[0]

@@ -23,6 +23,51 @@ def _maxrel(a, b):
 
 
 # ------------------------------------------------------------------------------------------------------------------ grid
+@pytest.mark.parametrize("layout,F", [("torch", 8), ("torch", 2), ("tcnn", 2), ("tcnn", 4)])
+@pytest.mark.parametrize("delta", [1.0 / 4096.0, 0.03])
+def test_grid_grouped_taps_equal_ungrouped(layout, F, delta):
+    """Encoding.point_groups(7): the numerical-gradient batch (sample + six +-delta taps, tap g of sample s at row g * N + s) through the
+    grouped kernels equals the ungrouped operator on the same points -- forward bit for bit, table gradient up to the order of the atomic
+    sums -- both when the taps share their cell (delta = finest-level cell) and when they do not (delta = 0.03), with masked levels."""
+    import sdfstudio_b200 as sb
+
+    L, log2T, base, scale = 8, 12, 8, 1.5
+    cfg = {"otype": "HashGrid", "n_levels": L, "n_features_per_level": F, "log2_hashmap_size": log2T, "base_resolution": base, "per_level_scale": scale,
+           "interpolation": "Linear"}
+    enc = sb.Encoding(3, cfg, layout=layout).cuda()
+    enc.set_active_levels(6)
+    g = torch.Generator().manual_seed(11)
+    with torch.no_grad():
+        enc.table.copy_(torch.randn(enc.table.shape, generator=g) * 0.3)
+    N = 1000
+    x = torch.rand(N, 3, generator=g) * 0.9 + 0.05
+    offs = torch.tensor([[0, 0, 0], [delta, 0, 0], [-delta, 0, 0], [0, delta, 0], [0, -delta, 0], [0, 0, delta], [0, 0, -delta]], dtype=torch.float32)
+    pts = (x[None] + offs[:, None, :]).reshape(-1, 3).cuda()
+    r = torch.randn(7 * N, L * F, generator=g).cuda()
+
+    def run(grouped):
+        enc.zero_grad(set_to_none=True)
+        if grouped:
+            with enc.point_groups(7):
+                out = enc(pts)
+        else:
+            out = enc(pts)
+        (out * r).sum().backward()
+        return out.detach(), enc.table.grad.detach().clone()
+
+    out_u, gt_u = run(False)
+    launches0 = sb._lib.launch_count()
+    out_g, gt_g = run(True)
+    assert sb._lib.launch_count() - launches0 == 2          # one grouped forward, one grouped backward
+    assert torch.equal(out_g, out_u)
+    assert float(out_u[:, 6 * F:].abs().max()) == 0.0 and float(out_u[:, : 6 * F].abs().max()) > 0
+    scale_g = float(gt_u.abs().max())
+    assert float((gt_g - gt_u).abs().max()) <= 2e-6 * scale_g, float((gt_g - gt_u).abs().max()) / scale_g
+    # a batch that is not a multiple of the group size falls back to the ungrouped kernels
+    with enc.point_groups(7):
+        assert torch.equal(enc(pts[:-1]), out_u[:-1])
+
+
 @pytest.mark.parametrize("layout", ["torch", "tcnn"])
 @pytest.mark.parametrize("smooth", [True, False])
 def test_grid_double_backward(layout, smooth):

@@ -87,7 +87,7 @@ def main(args):
     if world > 1:
         model = DDP(model, device_ids=[local_rank], find_unused_parameters=True, gradient_as_bucket_view=True)
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-15)
+    opt = torch.optim.Adam(params, lr=5e-4, eps=1e-15, fused=True)   # AdamOptimizerConfig(lr, eps) of method_configs.py:404-432; single-pass (fused) implementation
     R = R_TRAIN
     o, d, cam, nears, fars = dtu_like_rays(R, 2000 + rank)
     host = [t.pin_memory() for t in (o, d, nears, fars)]
