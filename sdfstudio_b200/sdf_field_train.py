@@ -79,11 +79,16 @@ def forward_geonetwork(field, inputs):
         feature = feature * field.hash_encoding_mask.to(feature.device)
     else:
         feature = torch.zeros_like(inputs[:, :1].repeat(1, field.encoding.n_output_dims))
-    pe = nerf_encoding(inputs, c.position_encoding_max_degree, c.position_encoding_max_degree - 1, False, c.off_axis)
-    if not c.use_position_encoding:
-        pe = torch.zeros_like(pe)
-    inputs = torch.cat((inputs, pe, feature), dim=-1)
-    x = inputs
+    if c.use_position_encoding:
+        pe = nerf_encoding(inputs, c.position_encoding_max_degree, c.position_encoding_max_degree - 1, False, c.off_axis)
+    else:                                                  # zeros of the encoding's shape (sdf_field.py:393-394) without evaluating it first
+        pe = inputs.new_zeros(inputs.shape[0], (21 if c.off_axis else 3) * 2 * c.position_encoding_max_degree)
+    parts = [inputs, pe, feature]
+    width = sum(t.shape[1] for t in parts)
+    if _gemm_precision(field) is not None and width % 16 != 0:
+        parts.append(inputs.new_zeros(inputs.shape[0], _lo.pad16(width) - width))     # the GEMMs' K padding, written by the same concatenation
+    x = torch.cat(parts, dim=-1)
+    inputs = x[:, :width]
     for l in range(0, field.num_layers - 1):
         lin = getattr(field, "glin" + str(l))
         if l in field.skip_in:
