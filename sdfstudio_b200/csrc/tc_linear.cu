@@ -1,7 +1,8 @@
 // Generic tensor-core Linear for the field shapes the fused kernel does not cover (bakedsdf / angelo / stock volsdf ...):
 //   Y[M, n0:n0+Nc] = epi( X[M, k0:k0+Kc] * W[n0:n0+Nc, k0:k0+Kc]^T (+ partial sums) + bias )
 // One CTA per 128-row tile, the machinery of the fused field kernel (and of the sdfb200_debug_tc_gemm building-block test):
-// 16 warps stage the fp32 activations as bf16 split planes straight into TMEM (A operand, TS mode), one warp streams the
+// 16 warps stage the fp32 activations as bf16 split planes straight into TMEM (A operand, TS mode; two 128-column halves, the MMAs of the
+// first half run while the second is staged), one warp streams the
 // pre-packed weight K-blocks through a 3-stage shared-memory ring with 1-D bulk copies, one thread issues tcgen05.mma (bf16x3 =
 // a0 w0 + a1 w0 + a0 w1, fp32 accumulate in TMEM), the 16 warps read D back and apply the epilogue of k_sgemm (field_simt.cu).
 // K > 256 / N > 256 are chunked by the host wrapper (partial sums round-trip through Y).
@@ -93,13 +94,21 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
     }
   } else if (warp == 17) {
     // ---------------- MMA issuer ----------------
-    bar_sync(1, kEpiL + 32);                 // A planes staged
+    // the A operand is staged in two 128-column halves: the MMAs of the first four K blocks run while the second half is still being
+    // converted (barrier 1: columns [0,128) staged, barrier 3: columns [128,256) staged)
+    bar_sync(1, kEpiL + 32);
     tc_fence_after();
-    if (lane == 0) {
+    {
       const uint32_t idesc = make_idesc_bf16(128, a.Ncp);
       const uint32_t lbo_b = (uint32_t)a.Ncp * 16, plane_b = (uint32_t)a.Ncp * kKBL * 2;
       uint32_t acc = 0;
       for (int b = 0; b < nblocks; ++b) {
+        if (b == 128 / kKBL) {               // warp-uniform: the whole warp takes part in the named barrier (reconverge first: bar.sync is .aligned)
+          __syncwarp();
+          bar_sync(3, kEpiL + 32);
+          tc_fence_after();
+        }
+        if (lane != 0) continue;
         const int s = b % kStagesL;
         mbar_wait(&full[s], (b / kStagesL) & 1);
         tc_fence_after();
@@ -118,7 +127,7 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
         }
         mma_commit(&empty[s]);
       }
-      mma_commit(&dfull);
+      if (lane == 0) mma_commit(&dfull);
     }
   } else {
     // ---------------- 16 warps: stage A, then the epilogue ----------------
@@ -162,11 +171,11 @@ __global__ void __launch_bounds__(kThreadsL, 1) k_tc_linear(const LinArgs a) {
         tmem_st8(a_tmem + lane_addr + kbase / 2 + g * 8, hi);
         if (P > 1) tmem_st8(a_tmem + 128 + lane_addr + kbase / 2 + g * 8, lo);
       }
-      bar_sync(2, kEpiL);                                   // the tile buffer is reused
+      // this half of the A operand is in TMEM: hand it to the MMA issuer (which also orders the reuse of the transposition tile)
+      tc_wait_st();
+      tc_fence_before();
+      bar_sync(kbase == 0 ? 1 : 3, kEpiL + 32);
     }
-    tc_wait_st();
-    tc_fence_before();
-    bar_sync(1, kEpiL + 32);
     mbar_wait_backoff(&dfull, 0);
     tc_fence_after();
     for (int nbase = 0; nbase < a.Ncp; nbase += 128) {
