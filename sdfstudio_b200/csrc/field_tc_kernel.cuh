@@ -11,7 +11,8 @@
 //   G0 G1    h = softplus_100(W a + b)       accumulator in TMEM (256 cols), converted IN PLACE into the next layer's A operand
 //            (bf16 planes, K step j at columns 16 j (hi) / 16 j + 8 (lo) of the accumulator it came from); the two 256-column halves
 //            of TMEM (X, Y) alternate as accumulator / A operand from layer to layer, and the next layer's MMAs TRAIL the epilogue:
-//            every 64 converted columns are handed to the MMA issuer (a_rdy[0..3]), so the tensor pipe runs under the epilogue
+//            every 32 converted columns (one streamed K block) are handed to the MMA issuer (a_rdy[0..7]), so the tensor pipe runs under
+//            the epilogue
 //   sdf      fp32 dot of h2 with row 0 of W2 on CUDA cores (exact fp32: the SDF drives NeuS alpha / Laplace density)
 //   (no G2)  the geo feature is linear in h2, so colour layer 0 is pre-multiplied at pack time: Wc = Wgf W2', and h2 itself
 //            (bf16 planes) takes the L2-resident round trip across the reverse sweep
@@ -22,7 +23,7 @@
 //   render   (fused mode) segmented prefix product over the rays of the tile in double, weights, per-ray sums
 // MMA = tcgen05.mma kind::f16 (bf16 x bf16 -> fp32).  bf16x3: a0*w0 + a1*w0 + a0*w1 with a = a0+a1, w = w0+w1
 // (error ~2^-16 relative, fp32 accumulate).  Weights stream through a shared-memory ring filled by 1-D bulk copies (UBLKCP)
-// from a pre-packed image.  Warp roles: 0-7 epilogues (2 threads per row: 128 columns each), 8-11 hash gathers, 12-13 PE / colour
+// from a pre-packed image.  Warp roles: 0-7 epilogues (2 threads per row: the 16-column chunks 2 i + q of iteration i), 8-11 hash gathers, 12-13 PE / colour
 // input columns, 14 weight producer, 15 MMA issuer (leader CTA) / weight-arrival relay (peer CTA).
 #pragma once
 #include "field_tc.h"
