@@ -265,3 +265,58 @@ def test_reference_tensordataclasses_pass_through_the_host_side():
     # FieldHeadNames of the reference compare equal to the product's keys (dicts returned by SDFField are indexed with either)
     assert {h.value for h in ref.FieldHeadNames} >= {h.value for h in sb.FieldHeadNames} or all(
         getattr(ref.FieldHeadNames, h.name).value == h.value for h in sb.FieldHeadNames)
+
+
+def test_grouped_grid_calls_reject_bad_groups_and_encoding_context_nests():
+    """host logic of the grouped grid operator: argument validation of the C entry points (no launch) and the Encoding.point_groups context."""
+    import sdfstudio_b200 as sb
+    from sdfstudio_b200 import _lib
+
+    lib = _lib.load()
+    enc = sb.HashEncoding(num_levels=4, min_res=4, max_res=32, log2_hashmap_size=8, features_per_level=2)
+    desc = enc._desc_ref()
+    # n not a multiple of the group size / NULL pointers: error codes, not crashes
+    assert lib.sdfb200_grid_encode_grouped(desc, None, None, 10, 7, None, 8, None) != 0
+    assert lib.sdfb200_grid_encode_grouped(desc, None, None, 14, 7, None, 8, None) != 0
+    assert lib.sdfb200_grid_encode_backward_grouped(desc, None, None, 14, 0, None, None) != 0
+    assert lib.sdfb200_grid_encode_grouped(desc, None, None, 0, 7, None, 8, None) == 0          # empty batch
+    assert enc._groups == 1
+    with enc.point_groups(7):
+        assert enc._groups == 7
+        with enc.point_groups(6):
+            assert enc._groups == 6
+        assert enc._groups == 7
+    assert enc._groups == 1
+
+
+def test_bench_train_section_reports_child_failures(monkeypatch):
+    """bench.py attaches the training step measured in child processes; a failing / hanging child must become an `error` entry of the
+    section, never an exception of the headline measurement."""
+    import subprocess
+    import sys
+
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class R:
+        returncode, stdout, stderr = 1, "", "Traceback ...\nRuntimeError: boom"
+
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: R())
+    out = bench.train_section(1, 0)
+    assert out["workload"] == "angelo-train-8192" and "boom" in out["error"]
+
+    def hang(*a, **k):
+        raise subprocess.TimeoutExpired(cmd="x", timeout=1)
+
+    monkeypatch.setattr(subprocess, "run", hang)
+    assert "timed out" in bench.train_section(2, 0)["error"]
+
+    class OK:
+        returncode, stderr = 0, ""
+        stdout = 'noise\n{"metric": "m", "value": 1.0, "unit": "rays/s", "n_gpus": 2, "steps": 5, "warmup": 3, "ms_per_step": 2.0, "config": {"rays_per_gpu": 8192, ' \
+                 '"parallelism": "dp", "gradient_bytes": 4, "allreduce_alone_ms": 0.5}, "e2e": {}, "gpu_launches": 3, "roofline": {}, "loss": 0.1}\n'
+
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: OK())
+    sec = bench.train_section(2, 0)
+    assert sec["value"] == 1.0 and sec["n_gpus"] == 2 and sec["allreduce_alone_ms"] == 0.5
+    assert bench.train_section(2, 1) is None                                                   # only rank 0 reports
