@@ -45,6 +45,14 @@ CASES: Dict[str, Tuple[FieldSpec, dict]] = {
     ),
 }
 
+# cases pinned on the CPU side only (oracle vs reference golden): they widen what the oracle is pinned on without adding GPU test shapes
+CPU_CASES: Dict[str, Tuple[FieldSpec, dict]] = {
+    # neus-facto shape behind the default (L2) SceneContraction (spatial_distortions.py:66-73, order=None), unbounded far plane
+    "neusfacto_l2": (
+        FieldSpec(num_layers=2, num_layers_color=2, hidden_dim=256, use_grid_feature=True, log2_hashmap_size=15, contraction="l2"),
+        dict(R=64, S=24, near=0.2, far=30.0, bias=0.5, beta_init=0.3, perturb=0.02, hash_init_scale=0.05, seed=6, spacing="piecewise"),
+    ),
+}
 
 def synthetic_rays(R: int, seed: int, radius: float = 2.7, dtype=torch.float32):
     """DTU-shaped synthetic rays: cameras on a sphere of radius ~2.7 looking at the origin
@@ -69,7 +77,7 @@ def synthetic_rays(R: int, seed: int, radius: float = 2.7, dtype=torch.float32):
 
 
 def case_inputs(name: str):
-    spec, kw = CASES[name]
+    spec, kw = CASES[name] if name in CASES else CPU_CASES[name]
     o, d, cam = synthetic_rays(kw["R"], kw["seed"] + 1000)
     nears = torch.full((kw["R"], 1), kw["near"])
     fars = torch.full((kw["R"], 1), kw["far"])

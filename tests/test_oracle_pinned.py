@@ -9,7 +9,7 @@ import torch
 from oracle import cases, render, samplers
 from oracle.field import OracleField, init_params
 
-FIELD_CASES = list(cases.CASES)
+FIELD_CASES = list(cases.CASES) + list(cases.CPU_CASES)      # CPU_CASES: oracle-vs-reference only (e.g. the L2 SceneContraction)
 SAMPLER_CASES = ["neusfacto_c1", "neusfacto_c1_init", "volsdf_stock"]
 
 
