@@ -52,6 +52,14 @@ CPU_CASES: Dict[str, Tuple[FieldSpec, dict]] = {
         FieldSpec(num_layers=2, num_layers_color=2, hidden_dim=256, use_grid_feature=True, log2_hashmap_size=15, contraction="l2"),
         dict(R=64, S=24, near=0.2, far=30.0, bias=0.5, beta_init=0.3, perturb=0.02, hash_init_scale=0.05, seed=6, spacing="piecewise"),
     ),
+    # branches of get_colors / the grid no other case combines (sdf_field.py:532-612): reflections + n.v WITHOUT the diffuse / tint heads,
+    # appearance embedding on, narrower MLPs (128 / 192 / 96), 3 colour layers, F = 4 linear hash grid, inside_outside geometry
+    "mixed_heads": (
+        FieldSpec(num_layers=2, num_layers_color=3, hidden_dim=128, hidden_dim_color=192, geo_feat_dim=96, use_grid_feature=True, num_levels=8, max_res=256,
+                  log2_hashmap_size=14, hash_features_per_level=4, hash_smoothstep=False, use_appearance_embedding=True, use_reflections=True, use_n_dot_v=True,
+                  position_encoding_max_degree=4),
+        dict(R=48, S=20, near=0.5, far=4.5, bias=0.6, beta_init=0.2, perturb=0.02, hash_init_scale=0.05, seed=7, inside_outside=True, spacing="lindisp"),
+    ),
 }
 
 def synthetic_rays(R: int, seed: int, radius: float = 2.7, dtype=torch.float32):
